@@ -1,0 +1,152 @@
+"""Generate ``tests/golden/*.npz`` by EXECUTING the unmodified reference (build container only).
+
+    python -m oracle.make_golden            # rewrites tests/golden/
+
+Each fixture stores the input frame, the physical spec, and what the reference's
+``Filter`` / ``Label`` produce for it through their own methods
+(filtering.py:910 ``_run_frame`` + :952 ``_mask_volume`` guarded as in :1014-1018;
+labelling.py:511 ``_compute_frame_thresholds`` + :538 ``_run_frame_full_volume``),
+plus per-sigma scalars recorded by wrapping (not modifying) the reference methods.
+The GPU box has no ``/root/reference``: tests there read only these files.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def _recording_filter(Filter):
+    class Rec(Filter):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.rec_gamma, self.rec_frob_thr, self.rec_max_abs, self.rec_mask_frac = [], [], [], []
+
+        def _calculate_gamma(self, g):
+            v = super()._calculate_gamma(g)
+            self.rec_gamma.append(float(v))
+            return v
+
+        def _get_frob_mask(self, frob):
+            # recover the threshold the reference derives, by its own helpers
+            if self.frob_thresh is None:
+                from nellie.utils.gpu_functions import otsu_threshold, triangle_threshold
+                pos = self._subsample_for_thresholds(frob)
+                thr = 0.0 if pos.size == 0 else float(min(triangle_threshold(pos, xp=np),
+                                                          otsu_threshold(pos, xp=np)[0]))
+            else:
+                thr = float(self.frob_thresh)
+            self.rec_frob_thr.append(thr)
+            m = super()._get_frob_mask(frob)
+            self.rec_mask_frac.append(float(m.mean()))
+            return m
+
+    return Rec
+
+
+def run_reference(raw, dim_res, no_z, filter_kwargs=None, label_kwargs=None, sigmas=None):
+    Filter, Label = ref_shim.load()
+    Rec = _recording_filter(Filter)
+    info = ref_shim.im_info_for(raw.shape, dim_res, no_z)
+    f = Rec(info, device="cpu", **(filter_kwargs or {}))
+    f._get_t()
+    f._set_default_sigmas()
+    if sigmas is not None:
+        f.sigmas = [float(s) for s in sigmas]
+        f.halo = f._compute_halo()
+    f.im_memmap = raw[None].copy()  # the reference mutates float32 inputs
+    pre = f._run_frame(0)
+    pre = np.array(pre, copy=True)
+    fin = f._mask_volume(pre.copy()) if float(np.sum(pre)) > 0.0 else pre.copy()
+    lab = Label(info, device="cpu", **(label_kwargs or {}))
+    lab.num_t = 1
+    it, ft = lab._compute_frame_thresholds(raw, fin)
+    labels = lab._run_frame_full_volume(0, raw, fin, it, ft)
+    return dict(
+        sigmas=np.asarray(f.sigmas, dtype=np.float64),
+        gamma=np.asarray(f.rec_gamma, dtype=np.float64),
+        frob_thr=np.asarray(f.rec_frob_thr, dtype=np.float64),
+        mask_frac=np.asarray(f.rec_mask_frac, dtype=np.float64),
+        frangi_pre=pre.astype(np.float32), frangi=fin.astype(np.float32),
+        intensity_thresh=np.float64(np.nan if it is None else it),
+        frangi_thresh=np.float64(np.nan if ft is None else ft),
+        min_area=np.int64(lab.min_area_pixels), labels=labels.astype(np.int32),
+    )
+
+
+def save_case(name, raw, dim_res, no_z, **kw):
+    out = run_reference(raw, dim_res, no_z, **kw)
+    meta = dict(dim_res=dim_res, no_z=bool(no_z),
+                filter_kwargs=kw.get("filter_kwargs") or {}, label_kwargs=kw.get("label_kwargs") or {},
+                explicit_sigmas=None if kw.get("sigmas") is None else [float(s) for s in kw["sigmas"]])
+    path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+    np.savez_compressed(path, raw=raw, meta=np.asarray(json.dumps(meta)), **out)
+    nz = int((out["frangi"] > 0).sum())
+    print(f"{name}: shape={raw.shape} sigmas={np.round(out['sigmas'], 3).tolist()} nonzero={nz} "
+          f"labels={int(out['labels'].max())} thr={float(out['frangi_thresh']):.6g} "
+          f"size={os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def label_only_cases():
+    """Direct ``Label._get_labels`` cases: hand-built responses with holes, specks and seams."""
+    _, Label = ref_shim.load()
+    rng = np.random.default_rng(11)
+    cases = {}
+    # 3-D: smooth random field thresholded into blobs, with carved cavities and specks
+    import scipy.ndimage as ndi
+    field = ndi.gaussian_filter(rng.standard_normal((20, 44, 48)), 2.0).astype(np.float32)
+    field = (field - field.min()) / (field.max() - field.min())
+    field[rng.random(field.shape) < 0.002] = 1.0          # specks (removed by the area filter)
+    field[8:11, 20:24, 20:24] = 0.0                        # cavity candidates
+    cases["label3d"] = (field.astype(np.float32), {"X": 0.2, "Y": 0.2, "Z": 0.3, "T": 1.0}, False, 0.55)
+    f2 = ndi.gaussian_filter(rng.standard_normal((72, 80)), 2.5).astype(np.float32)
+    f2 = (f2 - f2.min()) / (f2.max() - f2.min())
+    f2[rng.random(f2.shape) < 0.01] = 1.0
+    cases["label2d"] = (f2.astype(np.float32), {"X": 0.1, "Y": 0.1, "Z": None, "T": 1.0}, True, 0.6)
+    for name, (fr, dim_res, no_z, thr) in cases.items():
+        info = ref_shim.im_info_for(fr.shape, dim_res, no_z)
+        lab = Label(info, device="cpu")
+        lab.num_t = 1
+        labels = lab._run_frame_full_volume(0, fr, fr, None, thr)
+        meta = dict(dim_res=dim_res, no_z=no_z, frangi_thresh=thr)
+        path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+        np.savez_compressed(path, frangi=fr, labels=labels.astype(np.int32), min_area=np.int64(lab.min_area_pixels),
+                            meta=np.asarray(json.dumps(meta)))
+        print(f"{name}: shape={fr.shape} labels={int(labels.max())} min_area={lab.min_area_pixels}")
+
+
+def main():
+    from nellie_b200.phantoms import tubular_phantom_np
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    # (1) crop of the reference's own sample file, frame 0, its OME pixel sizes (BASELINE config #1)
+    vol = ref_shim.read_sample_frame(0)
+    save_case("sample_crop", np.ascontiguousarray(vol[:, 56:152, 96:208]), ref_shim.SAMPLE_DIM_RES, False)
+    # (2) isotropic 3-D phantom, default 5 sigmas
+    iso = {"X": 0.1, "Y": 0.1, "Z": 0.1, "T": 1.0}
+    save_case("phantom3d_iso", tubular_phantom_np((28, 60, 68), seed=21, n_tubes=6), iso, False)
+    # (3) anisotropic 3-D phantom with explicit sigma list (the config-#3 mechanism)
+    aniso = {"X": 0.1, "Y": 0.1, "Z": 0.2, "T": 1.0}
+    save_case("phantom3d_aniso", tubular_phantom_np((20, 52, 76), seed=22, n_tubes=5), aniso, False,
+              sigmas=[1.0, 1.4, 1.8, 2.2])
+    # (4) 2-D phantom: 2x2 closed-form eigenvalues + LoG blobness path (BASELINE config #4 shape class)
+    d2 = {"X": 0.1, "Y": 0.1, "Z": None, "T": 1.0}
+    save_case("phantom2d", tubular_phantom_np((150, 170), seed=23, n_tubes=7), d2, True)
+    # (5) > 1e6 voxels so the threshold lattice has strides > 1 (filtering.py:328-340); stored as uint8
+    big = tubular_phantom_np((40, 128, 200), seed=24, n_tubes=30)
+    big8 = np.clip(np.round(big / 2.0), 0, 255).astype(np.uint8)
+    save_case("phantom3d_strided", big8, iso, False, sigmas=[1.0, 1.6])
+    label_only_cases()
+
+
+if __name__ == "__main__":
+    main()

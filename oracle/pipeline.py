@@ -1,0 +1,532 @@
+"""Numpy/scipy restatement of nellie's Filter + Label hot path (TEST INFRASTRUCTURE ONLY).
+
+Every function cites the reference lines it restates (paths relative to the reference
+checkout, aelefebv/nellie @ 54bf227).  The arithmetic of this path lives in numpy and
+scipy.ndimage (third-party, pinned in the reference's ``uv.lock``: numpy 2.3.5, scipy
+1.16.3; this image has numpy 2.3.5 / scipy 1.18.1).  The restatement therefore calls the
+same library primitive at every reference call site, in the same dtype and the same
+order, so that it is bit-identical to the reference by construction; that claim is then
+*checked* against outputs of the executed reference (``tests/golden``, produced by
+``oracle/make_golden.py``).
+
+The functions are written as a flat, stateless pipeline (no ImInfo, no memmaps, no
+device ladder): input is one frame ``(Z, Y, X)`` or ``(Y, X)`` plus a :class:`FrameSpec`.
+Only the reference's full-volume (non-low-memory) branch is restated; the chunked
+branches compute different numbers and are not a parity target.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+import scipy.ndimage as ndi
+
+F32 = np.float32
+
+
+# --------------------------------------------------------------------------------------
+# configuration
+# --------------------------------------------------------------------------------------
+@dataclass
+class FrameSpec:
+    """Physical description of one frame; mirrors the ``im_info`` attributes the path reads
+    (``no_z``, ``dim_res``) plus the Filter/Label constructor knobs
+    (filtering.py:23-40, labelling.py:23-35)."""
+
+    dim_res: dict
+    no_z: bool = False
+    min_radius_um: float = 0.25
+    max_radius_um: float = 1.0
+    alpha_sq: float = 0.5
+    beta_sq: float = 0.5
+    frob_thresh: Optional[float] = None
+    frob_thresh_division: float = 2
+    max_threshold_samples: int = 1_000_000
+    truncate: float = 3.0
+    remove_edges: bool = False
+    sigmas: Optional[Sequence[float]] = None  # explicit override (BASELINE config #3)
+    # Label knobs
+    label_min_radius_um: float = 0.25
+    threshold_sampling_pixels: int = 1_000_000
+    histogram_nbins: int = 256
+    otsu_thresh_intensity: bool = False
+    threshold: Optional[float] = None
+
+    def spacing(self):
+        """filtering.py:265-275 (_get_spacing)."""
+        y = float(self.dim_res.get("Y") or 1.0)
+        x = float(self.dim_res.get("X") or 1.0)
+        if self.no_z:
+            return (y, x)
+        z = float(self.dim_res.get("Z") or self.dim_res.get("X") or 1.0)
+        return (z, y, x)
+
+    def z_ratio(self):
+        """filtering.py:75-78."""
+        z_res = self.dim_res.get("Z") or self.dim_res.get("X") or 1.0
+        x_res = self.dim_res.get("X") or 1.0
+        return float(z_res) / float(x_res)
+
+
+def sigma_schedule(spec: FrameSpec):
+    """filtering.py:88-89, :288-316 (_set_default_sigmas)."""
+    if spec.sigmas is not None:
+        return sorted(float(s) for s in spec.sigmas)
+    min_px = spec.min_radius_um / spec.dim_res["X"]
+    max_px = spec.max_radius_um / spec.dim_res["X"]
+    s_a, s_b = min_px / 2.0, max_px / 3.0
+    s_lo, s_hi = min(s_a, s_b), max(s_a, s_b)
+    if s_hi <= s_lo:
+        s_hi = s_lo + 0.2
+    step = max(0.2, (s_hi - s_lo) / 5.0)
+    out = list(np.arange(s_lo, s_hi, step, dtype=float))
+    out.sort()
+    return [float(s) for s in out]
+
+
+def sigma_vector(spec: FrameSpec, sigma: float):
+    """filtering.py:277-286 (_get_sigma_vec)."""
+    if spec.no_z:
+        return (float(sigma), float(sigma))
+    return (float(sigma) / spec.z_ratio(), float(sigma), float(sigma))
+
+
+def delta_sigma_vector(spec: FrameSpec, prev_sigma: float, sigma: float):
+    """filtering.py:816-825: per-axis incremental sigma of the cascade."""
+    out = []
+    for sp, sc in zip(sigma_vector(spec, prev_sigma), sigma_vector(spec, sigma)):
+        out.append(float(np.sqrt(max(0.0, float(sc) ** 2 - float(sp) ** 2))))
+    return tuple(out)
+
+
+def gaussian_radius(delta_sigma: float, truncate: float = 3.0) -> int:
+    """scipy.ndimage.gaussian_filter1d: ``lw = int(truncate * sd + 0.5)``."""
+    return int(truncate * float(delta_sigma) + 0.5)
+
+
+# --------------------------------------------------------------------------------------
+# F2 / U1 / U2 : sampling lattice and histogram thresholds
+# --------------------------------------------------------------------------------------
+def sample_strides(shape, max_samples):
+    """filtering.py:328-340 (_sample_strides)."""
+    nd = len(shape)
+    if max_samples is None or max_samples <= 0:
+        return (1,) * nd
+    total = int(np.prod(shape))
+    if total <= max_samples:
+        return (1,) * nd
+    s0 = max(1, int(np.ceil((total / max_samples) ** (1.0 / nd))))
+    st = [s0] * nd
+    while int(np.prod([int(np.ceil(n / s)) for n, s in zip(shape, st)])) > max_samples:
+        k = int(np.argmax([n / s for n, s in zip(shape, st)]))
+        st[k] += 1
+    return tuple(st)
+
+
+def lattice_positive(arr, max_samples):
+    """filtering.py:348-363 (_subsample_for_thresholds): strided lattice, keep > 0."""
+    if arr.size == 0:
+        return arr
+    st = sample_strides(arr.shape, max_samples)
+    sub = arr if all(s == 1 for s in st) else arr[tuple(slice(None, None, s) for s in st)]
+    sub = sub[sub > 0]
+    if sub.size > max_samples and sub.size > 0:  # never triggers; kept for fidelity
+        sub = sub[:: max(1, sub.size // max_samples)]
+    return sub
+
+
+def otsu(values, nbins=256):
+    """utils/gpu_functions.py:23-50 (otsu_threshold); returns the bin centre (f32)."""
+    flat = values.reshape(-1)
+    counts, edges = np.histogram(flat, bins=nbins, range=(flat.min(), flat.max()))
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    p = counts / np.sum(counts)
+    w_lo = np.cumsum(p)
+    m_lo = np.cumsum(p * centers) / w_lo
+    w_hi = np.cumsum(p[::-1])[::-1]
+    m_hi = (np.cumsum((p * centers)[::-1]) / w_hi[::-1])[::-1]
+    between = w_lo[:-1] * w_hi[1:] * (m_lo[:-1] - m_hi[1:]) ** 2
+    return centers[np.argmax(between)]
+
+
+def triangle(values, nbins=256):
+    """utils/gpu_functions.py:53-94 (triangle_threshold); returns the bin centre (f32)."""
+    flat = values.reshape(-1)
+    hist, edges = np.histogram(flat, bins=nbins, range=(np.min(flat), np.max(flat)))
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    hist = hist / np.sum(hist)
+    i_peak = np.argmax(hist)
+    h_peak = hist[i_peak]
+    i_lo, i_hi = np.flatnonzero(hist)[[0, -1]]
+    flipped = i_peak - i_lo < i_hi - i_peak
+    if flipped:
+        hist = np.flip(hist, axis=0)
+        i_lo = nbins - i_hi - 1
+        i_peak = nbins - i_peak - 1
+    width = i_peak - i_lo
+    xs = np.arange(width)
+    ys = hist[xs + i_lo]
+    nrm = np.sqrt(h_peak ** 2 + width ** 2)
+    h_peak = h_peak / nrm
+    width = width / nrm
+    i_lvl = np.argmax(h_peak * xs - width * ys) + i_lo
+    if flipped:
+        i_lvl = nbins - i_lvl - 1
+    return centers[i_lvl]
+
+
+def gamma_of(gauss, spec: FrameSpec) -> float:
+    """filtering.py:365-380 (_calculate_gamma)."""
+    pos = lattice_positive(gauss, spec.max_threshold_samples)
+    if pos.size == 0:
+        return float(np.finfo(np.float32).eps)
+    g = float(min(triangle(pos), otsu(pos)))
+    if g <= 0:
+        g = float(np.finfo(np.float32).eps)
+    return g
+
+
+# --------------------------------------------------------------------------------------
+# F1 : cascaded Gaussian
+# --------------------------------------------------------------------------------------
+def gauss_step(gauss, spec: FrameSpec, prev_sigma: float, sigma: float):
+    """filtering.py:827-835: in-place incremental blur prev_sigma -> sigma."""
+    dvec = delta_sigma_vector(spec, prev_sigma, sigma)
+    if any(s > 0 for s in dvec):
+        ndi.gaussian_filter(gauss, sigma=dvec, output=gauss, mode="reflect", cval=0.0,
+                            truncate=spec.truncate)
+    return gauss
+
+
+# --------------------------------------------------------------------------------------
+# F4 / F5 : finite-difference Hessian, Frobenius mask
+# --------------------------------------------------------------------------------------
+def hessian(gauss, spec: FrameSpec):
+    """filtering.py:446-562 (_compute_hessian, non-low-memory branch).
+
+    Returns (components dict in the reference's naming, frob_sq, max_abs, frob)."""
+    img = gauss.astype(F32, copy=False)
+    sp = spec.spacing()
+    if img.ndim == 2:
+        d0, d1 = np.gradient(img, *sp)
+        comp = {
+            "hxx": np.gradient(d0, sp[0], axis=0).astype(F32, copy=False),
+            "hxy": np.gradient(d0, sp[1], axis=1).astype(F32, copy=False),
+            "hyy": np.gradient(d1, sp[1], axis=1).astype(F32, copy=False),
+        }
+        frob_sq = comp["hxx"] ** 2 + comp["hyy"] ** 2 + 2.0 * (comp["hxy"] ** 2)
+    elif img.ndim == 3:
+        d0, d1, d2 = np.gradient(img, *sp)
+        comp = {
+            "hxx": np.gradient(d0, sp[0], axis=0).astype(F32, copy=False),
+            "hxy": np.gradient(d0, sp[1], axis=1).astype(F32, copy=False),
+            "hxz": np.gradient(d0, sp[2], axis=2).astype(F32, copy=False),
+            "hyy": np.gradient(d1, sp[1], axis=1).astype(F32, copy=False),
+            "hyz": np.gradient(d1, sp[2], axis=2).astype(F32, copy=False),
+            "hzz": np.gradient(d2, sp[2], axis=2).astype(F32, copy=False),
+        }
+        frob_sq = (comp["hxx"] ** 2 + comp["hyy"] ** 2 + comp["hzz"] ** 2
+                   + 2.0 * (comp["hxy"] ** 2 + comp["hxz"] ** 2 + comp["hyz"] ** 2))
+    else:
+        raise ValueError("frame must be 2-D or 3-D")
+    max_abs = 0.0
+    for c in comp.values():
+        if c.size > 0:
+            max_abs = max(max_abs, float(np.max(np.abs(c))))
+    if max_abs <= 0:
+        max_abs = 1.0
+    frob = np.sqrt(frob_sq) / max_abs
+    return comp, frob_sq, max_abs, frob
+
+
+def frob_threshold(frob, spec: FrameSpec) -> float:
+    """filtering.py:432-441: min(triangle, otsu) of the positive lattice sample (or fixed)."""
+    if spec.frob_thresh is not None:
+        return float(spec.frob_thresh)
+    pos = lattice_positive(frob, spec.max_threshold_samples)
+    if pos.size == 0:
+        return 0.0
+    return float(min(triangle(pos), otsu(pos)))
+
+
+def frob_mask(frob, spec: FrameSpec):
+    """filtering.py:407-444 (_get_frob_mask). Returns (mask, threshold_before_division)."""
+    inf = np.isinf(frob)
+    if np.any(inf):
+        fin = frob[~inf]
+        top = float(np.max(fin)) if fin.size > 0 else 0.0
+        frob = frob.copy()
+        frob[inf] = top
+    if not spec.frob_thresh_division:
+        return frob > 0, 0.0
+    thr = frob_threshold(frob, spec)
+    return frob > (thr / spec.frob_thresh_division), thr
+
+
+# --------------------------------------------------------------------------------------
+# F7 / F8 : eigenvalues and vesselness
+# --------------------------------------------------------------------------------------
+def eig_sorted_3d(comp, where):
+    """filtering.py:693-707 + :580-585: eigvalsh (f64 inside numpy, f32 result) sorted by |.|."""
+    h = np.stack([
+        np.stack([comp["hxx"][where], comp["hxy"][where], comp["hxz"][where]], axis=-1),
+        np.stack([comp["hxy"][where], comp["hyy"][where], comp["hyz"][where]], axis=-1),
+        np.stack([comp["hxz"][where], comp["hyz"][where], comp["hzz"][where]], axis=-1),
+    ], axis=-2)
+    ev = np.linalg.eigvalsh(h)
+    return np.take_along_axis(ev, np.argsort(np.abs(ev), axis=1), axis=1)
+
+
+def eig_sorted_2d(comp, where):
+    """filtering.py:676-690: closed-form 2x2, all float32."""
+    a, b, d = comp["hxx"][where], comp["hxy"][where], comp["hyy"][where]
+    tr = a + d
+    df = a - d
+    root = np.sqrt(df * df + 4.0 * (b * b))
+    lo = 0.5 * (tr - root)
+    hi = 0.5 * (tr + root)
+    swap = np.abs(lo) > np.abs(hi)
+    return np.stack([np.where(swap, hi, lo), np.where(swap, lo, hi)], axis=1)
+
+
+def vesselness(ev, spec: FrameSpec, gamma_sq: float):
+    """filtering.py:717-767 (_filter_hessian)."""
+    with np.errstate(all="ignore"):
+        if spec.no_z:
+            l1, l2 = ev[:, 0], ev[:, 1]
+            rb_sq = (np.abs(l1) / (np.abs(l2) + 1e-12)) ** 2
+            s_sq = l1 ** 2 + l2 ** 2
+            v = np.exp(-(rb_sq / spec.beta_sq)) * (1.0 - np.exp(-(s_sq / gamma_sq)))
+        else:
+            l1, l2, l3 = ev[:, 0], ev[:, 1], ev[:, 2]
+            ra_sq = (np.abs(l2) / (np.abs(l3) + 1e-12)) ** 2
+            rb_sq = (np.abs(l2) / (np.sqrt(np.abs(l2 * l3)) + 1e-12)) ** 2
+            s_sq = l1 ** 2 + l2 ** 2 + l3 ** 2
+            v = ((1.0 - np.exp(-(ra_sq / spec.alpha_sq)))
+                 * np.exp(-(rb_sq / spec.beta_sq))
+                 * (1.0 - np.exp(-(s_sq / gamma_sq))))
+    if not spec.no_z:
+        v[ev[:, 2] > 0] = 0.0
+    v[ev[:, 1] > 0] = 0.0
+    return np.nan_to_num(v, nan=0.0, posinf=0.0, neginf=0.0)
+
+
+def vesselness_volume(comp, mask, spec: FrameSpec, gamma_sq: float):
+    """filtering.py:651-715 (_compute_vesselness_chunkwise); chunking does not change values."""
+    where = np.where(mask)
+    out = np.zeros_like(next(iter(comp.values())), dtype=F32)
+    if where[0].size == 0:
+        return out
+    ev = eig_sorted_2d(comp, where) if spec.no_z else eig_sorted_3d(comp, where)
+    out[where] = vesselness(ev, spec, gamma_sq).astype(F32, copy=False)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# F9 / F10 : per-frame response
+# --------------------------------------------------------------------------------------
+def log_blobness(blurred, and_mask, spec: FrameSpec, sigmas):
+    """filtering.py:772-795 (_filter_log) — 2-D only; ``blurred`` is the sigma_max-blurred
+    frame because of the reference's aliasing."""
+    frame = blurred.astype(F32, copy=False)
+    acc = None
+    for i, s in enumerate(sigmas):
+        cur = -ndi.gaussian_laplace(frame, sigma_vector(spec, s)) * (float(s) ** 2)
+        cur = cur * and_mask
+        if i == 0:
+            acc = cur
+        else:
+            better = cur > acc
+            acc[better] = cur[better]
+    acc[acc < 0] = 0.0
+    top = np.max(acc)
+    return (acc / (top + 1e-12)) / 10.0
+
+
+def frangi_frame(frame, spec: FrameSpec, trace: Optional[list] = None):
+    """filtering.py:806-853 (_compute_vesselness) + :924-933 (_run_frame, full-volume).
+
+    ``trace`` (optional list) receives one dict per sigma with the intermediates the
+    CUDA kernels are checked against."""
+    sigmas = sigma_schedule(spec)
+    gauss = np.array(frame, dtype=F32, copy=True)  # never mutate the caller's array (App. C-1)
+    response = np.zeros_like(gauss, dtype=F32)
+    alive = np.ones_like(gauss, dtype=bool)
+    prev = 0.0
+    for s in sigmas:
+        gauss_step(gauss, spec, prev, s)
+        prev = s
+        gamma = gamma_of(gauss, spec)
+        gamma_sq = 2.0 * (float(gamma) ** 2)
+        comp, frob_sq, max_abs, frob = hessian(gauss, spec)
+        m, thr = frob_mask(frob, spec)
+        rec = None
+        if trace is not None:
+            rec = dict(sigma=s, gauss=gauss.copy(), gamma=gamma, gamma_sq=gamma_sq, max_abs=max_abs,
+                       frob_thr=thr, mask=m.copy(), comp={k: v.copy() for k, v in comp.items()},
+                       skipped=not bool(np.any(m)))
+            trace.append(rec)
+        if not np.any(m):
+            continue  # filtering.py:843-844 — note: the AND below is skipped too
+        v = vesselness_volume(comp, m, spec, gamma_sq)
+        if rec is not None:
+            rec["vessel"] = v.copy()
+        response = np.maximum(response, v)
+        alive &= m
+    out = response * alive
+    if spec.no_z:
+        blob = np.maximum(log_blobness(gauss, alive, spec, sigmas), 0)
+        out = np.maximum(out, blob)
+    if spec.remove_edges:
+        out = remove_edges(out, spec)
+    return out
+
+
+def _bbox_rows(sl):
+    rows = np.any(sl, axis=1)
+    cols = np.any(sl, axis=0)
+    if (not rows.any()) or (not cols.any()):
+        return 0, 0
+    r = np.where(rows)[0]
+    return int(r[0]), int(r[-1])
+
+
+def remove_edges(v, spec: FrameSpec):
+    """filtering.py:969-1000 (_remove_edges): zero 15-row bands at the bbox top/bottom."""
+    planes = [v] if spec.no_z else [v[z] for z in range(v.shape[0])]
+    for sl in planes:
+        if sl.size == 0:
+            continue
+        r0, r1 = _bbox_rows(sl)
+        height = max(0, r1 - r0 + 1)
+        if height <= 0:
+            continue
+        m = min(15, height)
+        sl[r0:r0 + m, :] = 0
+        sl[r1 - m + 1:r1 + 1, :] = 0
+    return v
+
+
+def finalize_mask(v, spec: FrameSpec):
+    """filtering.py:952-967 (_mask_volume) guarded as in :1014-1018 (_run_filter)."""
+    if not float(np.sum(v)) > 0.0:
+        return v
+    pos = lattice_positive(v, spec.max_threshold_samples)
+    if pos.size == 0:
+        return v
+    thr = np.percentile(pos, 1)
+    keep = ndi.binary_opening(v > thr)
+    return v * keep
+
+
+def filter_frame(frame, spec: FrameSpec, trace=None):
+    """One iteration of filtering.py:1007-1031 (_run_filter) without the memmap write."""
+    return finalize_mask(frangi_frame(frame, spec, trace=trace), spec)
+
+
+# --------------------------------------------------------------------------------------
+# Label (L1-L5)
+# --------------------------------------------------------------------------------------
+def label_min_radius_um(spec: FrameSpec) -> float:
+    """labelling.py:95-97."""
+    return max(float(spec.label_min_radius_um), float(spec.dim_res.get("X") or 1.0))
+
+
+def label_min_area(spec: FrameSpec) -> int:
+    """labelling.py:209-219 (_compute_min_area_pixels)."""
+    x = spec.dim_res.get("X") or 1.0
+    y = spec.dim_res.get("Y") or x
+    r = label_min_radius_um(spec)
+    if spec.no_z:
+        return max(1, int(np.ceil(np.pi * (r ** 2) / (float(x) * float(y)))))
+    z = spec.dim_res.get("Z") or x
+    vol = (4.0 / 3.0) * np.pi * (r ** 3)
+    return max(1, int(np.ceil(vol / (float(x) * float(y) * float(z)))))
+
+
+def label_sample(frame, spec: FrameSpec, gate_frame=None, gate_thresh=None):
+    """labelling.py:385-438 (_sample_nonzero)."""
+    flat = frame.reshape(-1)
+    if flat.size == 0:
+        return flat
+    gate = gate_frame.reshape(-1) if (gate_frame is not None and gate_thresh is not None) else None
+    step = max(int(flat.size) // max(1, int(spec.threshold_sampling_pixels)), 1)
+    offsets = (0, step // 2) if step > 1 and step // 2 > 0 else (0,)
+    vals = flat[:0]
+    for off in offsets:
+        s = flat[off::step]
+        if gate is not None:
+            vals = s[(s > 0) & (gate[off::step] > gate_thresh)]
+        else:
+            vals = s[s > 0]
+        if vals.size > 0 or step == 1:
+            return vals
+    if float(flat.max()) <= 0:
+        return vals
+    if gate is not None:
+        return flat[(flat > 0) & (gate > gate_thresh)]
+    return flat[flat > 0]
+
+
+def label_frangi_threshold(frangi, spec: FrameSpec, gate_frame=None, gate_thresh=None):
+    """labelling.py:440-455 (_compute_frangi_threshold)."""
+    vals = label_sample(frangi, spec, gate_frame, gate_thresh)
+    if vals.size == 0:
+        return None
+    lv = np.log10(vals)
+    t = 10 ** triangle(lv, nbins=spec.histogram_nbins)
+    o = 10 ** otsu(lv, nbins=spec.histogram_nbins)
+    return min(t, o)
+
+
+def label_thresholds(raw, frangi, spec: FrameSpec):
+    """labelling.py:511-532 (_compute_frame_thresholds)."""
+    it = None
+    if spec.otsu_thresh_intensity:
+        vals = label_sample(raw, spec)
+        it = otsu(vals, nbins=spec.histogram_nbins) if vals.size else 0
+    elif spec.threshold is not None:
+        it = spec.threshold
+    if it is not None:
+        return it, label_frangi_threshold(frangi, spec, gate_frame=raw, gate_thresh=it)
+    return it, label_frangi_threshold(frangi, spec)
+
+
+def label_frame(frangi, spec: FrameSpec, frangi_thresh, raw=None, intensity_thresh=None,
+                stages: Optional[dict] = None):
+    """labelling.py:467-509 (_get_labels) + :546-556 (_run_frame_full_volume)."""
+    frangi = np.asarray(frangi)
+    if intensity_thresh is not None:
+        frangi = frangi * (np.asarray(raw) > intensity_thresh)
+    structure = np.ones((3,) * frangi.ndim, dtype=bool)
+    mask = np.zeros_like(frangi, dtype=bool) if frangi_thresh is None else frangi > frangi_thresh
+    if not spec.no_z:
+        mask = ndi.binary_fill_holes(mask)
+    if stages is not None:
+        stages["filled"] = mask.copy()
+    labels, _ = ndi.label(mask, structure=structure)
+    if stages is not None:
+        stages["labels_first"] = labels.copy()
+    if labels.size == 0:
+        return labels
+    areas = np.bincount(labels.ravel())
+    if areas.size <= 1:
+        return labels
+    areas[0] = 0
+    keep = areas >= label_min_area(spec)
+    mask = keep[labels]
+    if stages is not None:
+        stages["kept"] = mask.copy()
+    mask = ndi.uniform_filter(mask.astype(F32), size=3) > 0.5
+    if stages is not None:
+        stages["smoothed"] = mask.copy()
+    labels, _ = ndi.label(mask, structure=structure)
+    return labels
+
+
+def segment_frame(raw, spec: FrameSpec):
+    """Filter then Label for one frame, as nellie.run does per timepoint (run.py:56-73)."""
+    fr = filter_frame(raw, spec)
+    it, ft = label_thresholds(raw, fr, spec)
+    return fr, label_frame(fr, spec, ft, raw=raw, intensity_thresh=it)
