@@ -1,0 +1,162 @@
+/* nellie_b200 — C ABI of the B200-native structure-enhancement hot path.
+ *
+ * Drop-in boundary for aelefebv/nellie @ 54bf227: the entry points below are what a binding
+ * of the reference's `Filter` (nellie/segmentation/filtering.py) and `Label`
+ * (nellie/segmentation/labelling.py) stage classes calls instead of numpy / scipy.ndimage /
+ * cupy (INTEGRATION.md shows the ctypes stub).  Each function names the reference lines it
+ * replaces.  Conventions:
+ *
+ *   - every pointer is a DEVICE pointer owned by the caller (contiguous, C order, T[Z]YX
+ *     frame layout), except arguments documented "host";
+ *   - no allocation happens inside the library; scratch space is passed in;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no host sync);
+ *   - return 0 on success, a negative NB200_ERR_* otherwise, text via nb200_last_error();
+ *   - scalars that the reference derives from the data (gamma, thresholds, max|H|) stay
+ *     in device memory between calls so a whole frame is enqueued without a round trip.
+ *
+ * Z window (multi-GPU slabs): a 3-D buffer holds `nz_buf` planes; buffer plane b is global
+ * plane b + zg_off of a frame with `nz_glob` planes; kernels compute planes [zc0, zc1)
+ * (buffer coordinates) and may read neighbouring planes that the caller filled by halo
+ * exchange.  Reflection (Gaussian) and one-sided differences (Hessian) apply at the GLOBAL
+ * frame border only.  Single GPU: nz_buf = nz_glob, zg_off = 0, zc0 = 0, zc1 = nz_buf.
+ * 2-D frames: nz = 1 with the `_2d` entry points.
+ */
+#ifndef NELLIE_B200_H
+#define NELLIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB200_ABI_VERSION 1
+
+#define NB200_OK 0
+#define NB200_ERR_ARG (-1)
+#define NB200_ERR_CUDA (-2)
+#define NB200_ERR_OOM (-3)          /* text contains "out of memory": nellie/utils/adaptive_run.py:116-127 */
+#define NB200_ERR_UNSUPPORTED (-4)
+
+/* geometry shared by the 3-D kernels */
+typedef struct nb200_vol {
+    int nz_buf, ny, nx; /* buffer extent */
+    int zc0, zc1;       /* planes to compute, buffer coordinates */
+    int zg_off;         /* global plane index of buffer plane 0 (may be negative) */
+    int nz_glob;        /* planes in the whole frame */
+} nb200_vol;
+
+/* value transforms applied while scanning a sample buffer */
+#define NB200_TF_NONE 0   /* v                       (gamma: gauss samples, filtering.py:369) */
+#define NB200_TF_DIV 1    /* v / *divisor            (frob: sqrt(frob_sq)/max_abs, filtering.py:562) */
+#define NB200_TF_LOG10 2  /* log10f(v)               (Label, labelling.py:450) */
+
+/* int64[NB200_HIST_WORDS] device state of one 256-bin histogram threshold */
+#define NB200_HIST_NBINS 256
+#define NB200_HIST_MIN 0    /* ordered key of the minimum kept value */
+#define NB200_HIST_MAX 1    /* ordered key of the maximum kept value */
+#define NB200_HIST_COUNT 2  /* number of kept values */
+#define NB200_HIST_BINS 3   /* 256 counts follow */
+#define NB200_HIST_WORDS (3 + NB200_HIST_NBINS)
+
+/* double[NB200_SP_WORDS] device record of the per-sigma scalars (filtering.py:839-848) */
+#define NB200_SP_GAMMA 0      /* min(triangle, otsu) of positive gauss samples, eps fallback */
+#define NB200_SP_GAMMA_SQ 1   /* 2*gamma^2 (f64, used as fl32) */
+#define NB200_SP_FROB_THR 2   /* min(triangle, otsu) of frob samples (before division) */
+#define NB200_SP_FROB_CUT 3   /* thr / frob_thresh_division: mask = frob > fl32(cut) */
+#define NB200_SP_MAX_ABS 4    /* max |Hessian component| (1.0 if <= 0) */
+#define NB200_SP_SKIP 5       /* 1.0 when the frob mask is empty: sigma skipped (filtering.py:843-844) */
+#define NB200_SP_STATUS 6     /* 0 ok, 1 degenerate histogram (reference would raise) */
+#define NB200_SP_TRI 7
+#define NB200_SP_OTSU 8
+#define NB200_SP_WORDS 12
+
+/* int64[NB200_HS_WORDS] device record reduced by nb200_hessian_stats */
+#define NB200_HS_MAX_ABS_BITS 0   /* float bits of max|H| */
+#define NB200_HS_MAX_FROBSQ_BITS 1 /* float bits of max frob_sq */
+#define NB200_HS_WORDS 2
+
+int nb200_abi_version(void);
+const char* nb200_last_error(void);
+/* number of SMs of the current device (grid sizing is a multiple of it) */
+int nb200_sm_count(void);
+
+/* ---- F1: cascaded Gaussian --------------------------------------------------------------
+ * One axis of scipy.ndimage.gaussian_filter(mode="reflect") as called at filtering.py:828-835:
+ * float32 in, float64 accumulate in scipy's pair order, float32 out.  `weights` (HOST, double)
+ * holds w[0..radius], w[0] the centre tap, normalised as scipy's _gaussian_kernel1d does.
+ * axis: 0 = Z, 1 = Y, 2 = X.  src != dst. */
+int nb200_gauss_axis(const float* src, float* dst, const nb200_vol* vol, int axis,
+                     const double* weights, int radius, void* stream);
+
+/* ---- F2: threshold sampling lattice -----------------------------------------------------
+ * arr[::sz, ::sy, ::sx] on the GLOBAL lattice (filtering.py:328-363); every lattice point of
+ * the planes [zc0,zc1) is written (consumers keep values > 0).  `out` holds
+ * n_lattice_planes * ceil(ny/sy) * ceil(nx/sx) floats, planes in ascending z. */
+int nb200_lattice_sample(const float* src, const nb200_vol* vol, int sz, int sy, int sx,
+                         float* out, void* stream);
+/* flat[offset::step] of a contiguous array (labelling.py:412), n_out = ceil((n-offset)/step);
+ * if gate != NULL, values whose gate[i] <= gate_thresh are written as 0 (labelling.py:417). */
+int nb200_strided_sample(const float* src, long long n, long long offset, long long step,
+                         const float* gate, float gate_thresh, float* out, void* stream);
+
+/* ---- U1/U2: 256-bin histogram thresholds (utils/gpu_functions.py:23-94) -------------------
+ * hist_reset zeroes the state; hist_minmax folds min/max/count of the kept (> 0) transformed
+ * values; hist_bins adds np.histogram(bins=256, range=(min,max)) counts (float32 edges with
+ * numpy's edge correction).  Between the calls a multi-GPU caller all-reduces the state
+ * (MIN/MAX/SUM per field). `divisor` is a device double* (NB200_TF_DIV) or NULL. */
+int nb200_hist_reset(long long* state, void* stream);
+int nb200_hist_minmax(const float* vals, long long n, int transform, const double* divisor,
+                      long long* state, void* stream);
+int nb200_hist_bins(const float* vals, long long n, int transform, const double* divisor,
+                    long long* state, void* stream);
+/* gamma = min(triangle, otsu) (filtering.py:365-380) -> sp[GAMMA], sp[GAMMA_SQ] */
+int nb200_finalize_gamma(const long long* state, double* sp, void* stream);
+/* Frobenius threshold (filtering.py:407-444): consumes the histogram of frob samples and the
+ * reduced Hessian stats; fixed_thresh = NaN for auto. -> sp[FROB_THR..SKIP] */
+int nb200_finalize_frob(const long long* state, const long long* hstats, double fixed_thresh,
+                        double division, double* sp, void* stream);
+/* max|H| -> sp[MAX_ABS] (must run before hist_* with NB200_TF_DIV on &sp[MAX_ABS]) */
+int nb200_finalize_max_abs(const long long* hstats, double* sp, void* stream);
+/* Label threshold (labelling.py:440-455): out[0] = min(10**tri, 10**otsu) as float32 value,
+ * out[1] = 10**tri, out[2] = 10**otsu, out[3] = 1 if no samples (None), out[4] = status.
+ * With log_domain = 0 it is the plain Otsu of labelling.py:457-465 (out[0] = otsu). */
+int nb200_finalize_label_threshold(const long long* state, int log_domain, double* out, void* stream);
+
+/* ---- F4: Hessian statistics -------------------------------------------------------------
+ * Finite-difference Hessian of numpy.gradient(numpy.gradient(.)) (filtering.py:446-562) at
+ * every voxel of [zc0,zc1): reduces max|component| and max frob_sq into hstats and writes
+ * sqrt(frob_sq) at the lattice points into `frob_samples` (layout of nb200_lattice_sample).
+ * spacing[6] (HOST, float): {fl32(hz), fl32(2hz), fl32(hy), fl32(2hy), fl32(hx), fl32(2hx)}. */
+int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* spacing,
+                        int sz, int sy, int sx, float* frob_samples, long long* hstats, void* stream);
+int nb200_hstats_reset(long long* hstats, void* stream);
+
+/* ---- F4-F9 fused: Hessian + Frobenius mask + eigenvalues + vesselness + max/AND ------------
+ * (filtering.py:842-851).  acc holds max-over-sigma vesselness for live voxels and -1 for
+ * voxels that failed the mask at any non-skipped sigma; acc must be zero-filled before the
+ * first sigma.  Reads gamma_sq / frob cut / max_abs / skip from the device record `sp`. */
+int nb200_frangi_accumulate(const float* gauss, float* acc, const nb200_vol* vol, const float* spacing,
+                            float alpha_sq, float beta_sq, const double* sp, void* stream);
+/* 2-D variant (closed-form 2x2 eigenvalues, filtering.py:676-690, :737-741); spacing[4] = y,x */
+int nb200_frangi_accumulate_2d(const float* gauss, float* acc, int ny, int nx, const float* spacing,
+                               float beta_sq, const double* sp, void* stream);
+int nb200_hessian_stats_2d(const float* gauss, int ny, int nx, const float* spacing, int sy, int sx,
+                           float* frob_samples, long long* hstats, void* stream);
+
+/* ---- F11: percentile + opening ----------------------------------------------------------
+ * np.percentile(positive lattice sample, 1) (filtering.py:963) by radix select; scratch is
+ * int64[2048+8] device words; out[0] = threshold, out[1] = number of positive samples. */
+int nb200_percentile(const float* samples, long long n, double q_percent, long long* scratch,
+                     double* out, void* stream);
+/* out = V * binary_opening(V > thr) with V = max(acc, 0) (filtering.py:926, :964-966); cross
+ * structuring element, border_value 0.  If out_thr[1] == 0 (no positive sample) V passes
+ * through unchanged (filtering.py:959-960).  Needs 2 halo planes of acc on interior slab sides. */
+int nb200_finalize_opening(const float* acc, float* out, const nb200_vol* vol, const double* thr, void* stream);
+int nb200_finalize_opening_2d(const float* v, float* out, int ny, int nx, const double* thr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NELLIE_B200_H */

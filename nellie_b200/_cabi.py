@@ -1,0 +1,103 @@
+"""ctypes binding of ``csrc/libnellie_b200.so`` (the C ABI declared in ``include/nellie_b200.h``).
+
+There is deliberately no CPU fallback: if the shared library is missing or a call fails, the
+product path raises.  (``nellie_b200.build.build()`` compiles it in-tree with nvcc.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+HIST_WORDS = 3 + 256
+SP_WORDS = 12
+HS_WORDS = 2
+SP_GAMMA, SP_GAMMA_SQ, SP_FROB_THR, SP_FROB_CUT, SP_MAX_ABS, SP_SKIP, SP_STATUS, SP_TRI, SP_OTSU = range(9)
+TF_NONE, TF_DIV, TF_LOG10 = 0, 1, 2
+SELECT_WORDS = 2048 + 8
+
+ERR_OOM = -3
+
+
+class Vol(C.Structure):
+    """``nb200_vol``: Z-window geometry shared by the 3-D kernels."""
+    _fields_ = [("nz_buf", C.c_int), ("ny", C.c_int), ("nx", C.c_int), ("zc0", C.c_int), ("zc1", C.c_int),
+                ("zg_off", C.c_int), ("nz_glob", C.c_int)]
+
+    @classmethod
+    def whole(cls, nz, ny, nx):
+        return cls(nz, ny, nx, 0, nz, 0, nz)
+
+
+class NellieB200Error(RuntimeError):
+    pass
+
+
+class NellieB200OutOfMemory(MemoryError):
+    """Raised for NB200_ERR_OOM so the reference's retry ladder (adaptive_run.is_oom_error) sees it."""
+
+
+_p = C.c_void_p
+_ll = C.c_longlong
+_SIGS = {
+    "nb200_abi_version": ([], C.c_int),
+    "nb200_last_error": ([], C.c_char_p),
+    "nb200_sm_count": ([], C.c_int),
+    "nb200_gauss_axis": ([_p, _p, C.POINTER(Vol), C.c_int, C.POINTER(C.c_double), C.c_int, _p], C.c_int),
+    "nb200_lattice_sample": ([_p, C.POINTER(Vol), C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
+    "nb200_strided_sample": ([_p, _ll, _ll, _ll, _p, C.c_float, _p, _p], C.c_int),
+    "nb200_hist_reset": ([_p, _p], C.c_int),
+    "nb200_hist_minmax": ([_p, _ll, C.c_int, _p, _p, _p], C.c_int),
+    "nb200_hist_bins": ([_p, _ll, C.c_int, _p, _p, _p], C.c_int),
+    "nb200_finalize_gamma": ([_p, _p, _p], C.c_int),
+    "nb200_finalize_frob": ([_p, _p, C.c_double, C.c_double, _p, _p], C.c_int),
+    "nb200_finalize_max_abs": ([_p, _p, _p], C.c_int),
+    "nb200_finalize_label_threshold": ([_p, C.c_int, _p, _p], C.c_int),
+    "nb200_hessian_stats": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, _p, _p, _p], C.c_int),
+    "nb200_hstats_reset": ([_p, _p], C.c_int),
+    "nb200_frangi_accumulate": ([_p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_float, C.c_float, _p, _p], C.c_int),
+    "nb200_frangi_accumulate_2d": ([_p, _p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, _p, _p], C.c_int),
+    "nb200_hessian_stats_2d": ([_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, _p, _p, _p], C.c_int),
+    "nb200_percentile": ([_p, _ll, C.c_double, _p, _p, _p], C.c_int),
+    "nb200_finalize_opening": ([_p, _p, C.POINTER(Vol), _p, _p], C.c_int),
+    "nb200_finalize_opening_2d": ([_p, _p, C.c_int, C.c_int, _p, _p], C.c_int),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (once) and return the ctypes library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise NellieB200Error(
+            f"{path} is missing: build it with `python -m nellie_b200.build` (nvcc, sm_100a). "
+            "nellie_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (argtypes, restype) in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc == 0:
+        return
+    msg = load().nb200_last_error().decode("utf-8", "replace")
+    if rc == ERR_OOM:
+        raise NellieB200OutOfMemory(f"CUDA out of memory in {what}: {msg}")
+    raise NellieB200Error(f"{what} failed ({rc}): {msg}")
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)

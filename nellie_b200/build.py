@@ -1,0 +1,68 @@
+"""In-tree build of ``csrc/libnellie_b200.so`` for sm_100a (nvcc cross-compiles without a GPU).
+
+``--fmad=false``: numpy never contracts a multiply with an add across ufuncs, so parity-critical
+float arithmetic must not be fused by the compiler; fused operations are explicit fma()/fmaf().
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libnellie_b200.so")
+SOURCES = ["cabi.cu", "gauss.cu", "thresholds.cu", "frangi.cu", "finalize.cu", "label.cu", "log2d.cu"]
+HEADERS = ["common.cuh", "devmath.cuh", "hessian.cuh", os.path.join("..", "..", "include", "nellie_b200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
+              "-std=c++17", "-Xcompiler", "-fPIC",
+              "--expt-relaxed-constexpr", "--expt-extended-lambda"]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; cannot build libnellie_b200.so")
+    return exe
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu to an object and link the shared library; returns its path."""
+    nvcc = _nvcc()
+    hdrs = [os.path.join(CSRC, h) for h in HEADERS]
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    objs = []
+    procs = []
+    for s in srcs:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _stale(obj, [src, os.path.abspath(__file__)] + hdrs):
+            cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for name, p in procs:
+        out, _ = p.communicate()
+        if verbose and out:
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {name}:\n{out}")
+    if force or procs or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,520 @@
+// F2 / F3 / F5 / U1 / U2 / L2 / L3 — sampling lattice and 256-bin histogram thresholds, on device.
+//
+// Reference: nellie/segmentation/filtering.py:328-380, :407-444; nellie/utils/gpu_functions.py:23-94;
+// nellie/segmentation/labelling.py:385-465.  Exact numpy semantics restated in SURVEY.md A.3/A.4:
+// np.histogram with float32 scalars builds float32 edges with np.linspace and corrects the
+// computed bin index against the edges; Otsu / triangle run in float64 with sequential
+// cumulative sums.  The scalars never leave the device: the next kernel reads them from `sp`.
+#include "common.cuh"
+#include "devmath.cuh"
+
+namespace {
+
+constexpr int NB = NB200_HIST_NBINS;
+
+// ------------------------------------------------------------------------------------------
+// sampling
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+lattice_sample_kernel(const float* __restrict__ src, nb200_vol v, int sz, int sy, int sx, int g_first,
+                      int n_lat_z, int ly, int lx, float* __restrict__ out) {
+    const long long total = (long long)n_lat_z * ly * lx;
+    const long long plane = (long long)v.ny * v.nx;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int kz = (int)(i / ((long long)ly * lx));
+        const int rem = (int)(i - (long long)kz * ly * lx);
+        const int ky = rem / lx, kx = rem - ky * lx;
+        const int zb = g_first + kz * sz - v.zg_off;
+        out[i] = __ldg(src + (long long)zb * plane + (long long)(ky * sy) * v.nx + kx * sx);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+strided_sample_kernel(const float* __restrict__ src, long long n_out, long long offset, long long step,
+                      const float* __restrict__ gate, float gate_thresh, float* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_out;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long j = offset + i * step;
+        float val = __ldg(src + j);
+        if (gate != nullptr && !(__ldg(gate + j) > gate_thresh)) val = 0.0f;
+        out[i] = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// histogram state
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool transformed(float raw, int tf, float divisor, float& out) {
+    // keep rule of the reference: arr[arr > 0] on the array the histogram is taken of
+    if (tf == NB200_TF_DIV) {
+        const float q = raw / divisor;   // frob = sqrt(frob_sq) / max_abs  (filtering.py:562)
+        if (!(q > 0.0f)) return false;
+        out = q;
+        return true;
+    }
+    if (!(raw > 0.0f)) return false;
+    out = (tf == NB200_TF_LOG10) ? log10f(raw) : raw;
+    return true;
+}
+
+__global__ void hist_reset_kernel(long long* state) {
+    const int i = threadIdx.x + blockIdx.x * blockDim.x;
+    if (i >= NB200_HIST_WORDS) return;
+    long long val = 0;
+    if (i == NB200_HIST_MIN) val = 0xffffffffLL;
+    state[i] = val;
+}
+
+__global__ void __launch_bounds__(256)
+hist_minmax_kernel(const float* __restrict__ vals, long long n, int tf, const double* __restrict__ divisor,
+                   long long* __restrict__ state) {
+    const float dv = divisor ? (float)(*divisor) : 1.0f;
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    unsigned long long cnt = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float t;
+        if (transformed(__ldg(vals + i), tf, dv, t)) {
+            const uint32_t k = nb::float_to_ordered(t);
+            lo = min(lo, k);
+            hi = max(hi, k);
+            ++cnt;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    __shared__ uint32_t s_lo[8], s_hi[8];
+    __shared__ unsigned long long s_cnt[8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_lo[w] = lo; s_hi[w] = hi; s_cnt[w] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            lo = min(lo, s_lo[k]); hi = max(hi, s_hi[k]); cnt += s_cnt[k];
+        }
+        if (cnt) {
+            atomicMin((unsigned long long*)&state[NB200_HIST_MIN], (unsigned long long)lo);
+            atomicMax((unsigned long long*)&state[NB200_HIST_MAX], (unsigned long long)hi);
+            atomicAdd((unsigned long long*)&state[NB200_HIST_COUNT], cnt);
+        }
+    }
+}
+
+// float32 bin edges exactly as np.linspace(first, last, 257, dtype=float32) builds them
+__device__ void build_edges(float first, float last, float* edges /*NB+1*/, int tid, int nthreads) {
+    if (first == last) { first = first - 0.5f; last = last + 0.5f; }  // numpy _get_outer_edges
+    const float delta = last - first;
+    const float step = delta / (float)NB;
+    for (int i = tid; i <= NB; i += nthreads) {
+        float y = (float)i;
+        if (step == 0.0f) { y = y / (float)NB; y = y * delta; }
+        else y = y * step;
+        y = y + first;
+        if (i == NB) y = last;
+        edges[i] = y;
+    }
+}
+
+__device__ __forceinline__ void outer_edges(const long long* state, float& first, float& last) {
+    first = nb::ordered_to_float((uint32_t)state[NB200_HIST_MIN]);
+    last = nb::ordered_to_float((uint32_t)state[NB200_HIST_MAX]);
+}
+
+__global__ void __launch_bounds__(256)
+hist_bins_kernel(const float* __restrict__ vals, long long n, int tf, const double* __restrict__ divisor,
+                 long long* __restrict__ state) {
+    __shared__ float edges[NB + 1];
+    __shared__ unsigned int local[NB];
+    if (state[NB200_HIST_COUNT] == 0) return;
+    float first, last;
+    outer_edges(state, first, last);
+    build_edges(first, last, edges, threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < NB; i += blockDim.x) local[i] = 0;
+    __syncthreads();
+    const float e_first = edges[0], e_last = edges[NB];
+    const float denom = e_last - e_first;
+    const float dv = divisor ? (float)(*divisor) : 1.0f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float t;
+        if (!transformed(__ldg(vals + i), tf, dv, t)) continue;
+        if (!(t >= e_first) || !(t <= e_last)) continue;
+        // numpy _histogram: index from the scaled offset, then the +-1 edge correction
+        const float f = ((t - e_first) / denom) * (float)NB;
+        int b = (int)f;
+        if (b == NB) b = NB - 1;
+        if (t < edges[b]) --b;
+        else if (t >= edges[b + 1] && b != NB - 1) ++b;
+        atomicAdd(&local[b], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NB; i += blockDim.x)
+        if (local[i]) atomicAdd((unsigned long long*)&state[NB200_HIST_BINS + i], (unsigned long long)local[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Otsu + triangle on the 256 counts (float64, sequential cumulative sums like np.cumsum)
+// ------------------------------------------------------------------------------------------
+struct TwoThresholds {
+    float tri, otsu;
+    int status;  // 0 ok, 1 degenerate (reference raises / yields NaN)
+};
+
+__device__ TwoThresholds otsu_triangle(const long long* state, double* work /* >= 4*NB doubles */) {
+    TwoThresholds r; r.tri = 0.f; r.otsu = 0.f; r.status = 0;
+    float first, last;
+    outer_edges(state, first, last);
+    __shared__ float edges[NB + 1];
+    __shared__ float centers[NB];
+    build_edges(first, last, edges, 0, 1);
+    for (int i = 0; i < NB; ++i) centers[i] = (edges[i] + edges[i + 1]) / 2.0f;
+    double* p = work;            // normalised counts
+    double* w_hi = work + NB;    // reverse cumulative weight
+    double* s_hi = work + 2 * NB;  // reverse cumulative p*c
+    long long total = 0;
+    for (int i = 0; i < NB; ++i) total += state[NB200_HIST_BINS + i];
+    const double dt = (double)total;
+    for (int i = 0; i < NB; ++i) p[i] = (double)state[NB200_HIST_BINS + i] / dt;
+    // ---- Otsu (gpu_functions.py:36-50)
+    {
+        double aw = 0.0, as = 0.0;
+        for (int i = NB - 1; i >= 0; --i) {
+            aw = aw + p[i];
+            as = as + p[i] * (double)centers[i];
+            w_hi[i] = aw;
+            s_hi[i] = as;
+        }
+        double w_lo = 0.0, s_lo = 0.0, best = 0.0;
+        int arg = 0;
+        bool have = false, nan_hit = false;
+        for (int i = 0; i < NB - 1; ++i) {
+            w_lo = w_lo + p[i];
+            s_lo = s_lo + p[i] * (double)centers[i];
+            const double m_lo = s_lo / w_lo;
+            const double m_hi = s_hi[i + 1] / w_hi[i + 1];
+            const double d = m_lo - m_hi;
+            const double var = (w_lo * w_hi[i + 1]) * (d * d);
+            if (var != var) {  // np.argmax returns the first NaN
+                if (!nan_hit) { arg = i; nan_hit = true; }
+            } else if (!nan_hit && (!have || var > best)) {
+                best = var; arg = i; have = true;
+            }
+        }
+        if (nan_hit) r.status = 1;
+        r.otsu = centers[arg];
+    }
+    // ---- triangle (gpu_functions.py:65-94)
+    {
+        int peak = 0;
+        double hpk = p[0];
+        for (int i = 1; i < NB; ++i) if (p[i] > hpk) { hpk = p[i]; peak = i; }
+        int lo = 0, hi = NB - 1;
+        while (lo < NB - 1 && !(p[lo] != 0.0)) ++lo;
+        while (hi > 0 && !(p[hi] != 0.0)) --hi;
+        const bool flip = (peak - lo) < (hi - peak);
+        if (flip) { lo = NB - hi - 1; peak = NB - peak - 1; }
+        const int width = peak - lo;
+        if (width <= 0) {
+            r.status = 1;  // np.argmax of an empty array raises ValueError in the reference
+            r.tri = centers[flip ? NB - lo - 1 : lo];
+        } else {
+            const double nrm = sqrt(hpk * hpk + (double)((long long)width * width));
+            const double hn = hpk / nrm, wn = (double)width / nrm;
+            double best = 0.0; int arg = 0;
+            for (int x = 0; x < width; ++x) {
+                const int src = x + lo;
+                const double y = flip ? p[NB - 1 - src] : p[src];
+                const double len = hn * (double)x - wn * y;
+                if (x == 0 || len > best) { best = len; arg = x; }
+            }
+            int lvl = arg + lo;
+            if (flip) lvl = NB - lvl - 1;
+            r.tri = centers[lvl];
+        }
+    }
+    return r;
+}
+
+__global__ void finalize_gamma_kernel(const long long* state, double* sp) {
+    __shared__ double work[4 * NB];
+    if (threadIdx.x != 0) return;
+    const double eps = 1.1920928955078125e-07;  // np.finfo(np.float32).eps
+    double gamma = eps;
+    double status = 0.0;
+    if (state[NB200_HIST_COUNT] > 0) {
+        const TwoThresholds t = otsu_triangle(state, work);
+        sp[NB200_SP_TRI] = (double)t.tri;
+        sp[NB200_SP_OTSU] = (double)t.otsu;
+        gamma = (double)fminf(t.tri, t.otsu);
+        if (t.tri != t.tri || t.otsu != t.otsu) gamma = (double)(t.tri + t.otsu);
+        if (gamma <= 0.0) gamma = eps;
+        status = (double)t.status;
+    }
+    sp[NB200_SP_GAMMA] = gamma;
+    sp[NB200_SP_GAMMA_SQ] = 2.0 * (gamma * gamma);
+    sp[NB200_SP_STATUS] = status;
+}
+
+__global__ void finalize_max_abs_kernel(const long long* hstats, double* sp) {
+    if (threadIdx.x != 0) return;
+    float m = nb::u2f((uint32_t)hstats[NB200_HS_MAX_ABS_BITS]);
+    if (!(m > 0.0f)) m = 1.0f;  // filtering.py:560-561
+    sp[NB200_SP_MAX_ABS] = (double)m;
+}
+
+__global__ void finalize_frob_kernel(const long long* state, const long long* hstats, double fixed_thresh,
+                                     double division, double* sp) {
+    __shared__ double work[4 * NB];
+    if (threadIdx.x != 0) return;
+    double thr = 0.0;
+    double status = sp[NB200_SP_STATUS];
+    if (fixed_thresh == fixed_thresh) {
+        thr = fixed_thresh;
+    } else if (state[NB200_HIST_COUNT] > 0) {
+        const TwoThresholds t = otsu_triangle(state, work);
+        thr = (double)fminf(t.tri, t.otsu);
+        if (t.status) status = 1.0;
+    }
+    const float max_abs = (float)sp[NB200_SP_MAX_ABS];
+    const float top = sqrtf(nb::u2f((uint32_t)hstats[NB200_HS_MAX_FROBSQ_BITS])) / max_abs;
+    double cut;
+    bool any;
+    if (division == 0.0) {       // filtering.py:428-430: mask = frob > 0
+        cut = 0.0;
+    } else {
+        cut = thr / division;
+    }
+    any = top > (float)cut;     // sqrt and division are monotone: max frob decides emptiness
+    sp[NB200_SP_FROB_THR] = thr;
+    sp[NB200_SP_FROB_CUT] = cut;
+    sp[NB200_SP_SKIP] = any ? 0.0 : 1.0;
+    sp[NB200_SP_STATUS] = status;
+}
+
+__global__ void finalize_label_kernel(const long long* state, int log_domain, double* out) {
+    __shared__ double work[4 * NB];
+    if (threadIdx.x != 0) return;
+    out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; out[3] = 1.0; out[4] = 0.0;
+    if (state[NB200_HIST_COUNT] <= 0) return;
+    const TwoThresholds t = otsu_triangle(state, work);
+    out[3] = 0.0;
+    out[4] = (double)t.status;
+    if (log_domain) {
+        // 10 ** np.float32 -> float32 power; evaluate in f64 and round once (labelling.py:452-455)
+        const float a = (float)pow(10.0, (double)t.tri);
+        const float b = (float)pow(10.0, (double)t.otsu);
+        out[1] = (double)a;
+        out[2] = (double)b;
+        out[0] = (double)fminf(a, b);
+    } else {
+        out[1] = (double)t.tri;
+        out[2] = (double)t.otsu;
+        out[0] = (double)t.otsu;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// percentile by 3-pass radix select over the positive samples (F11, filtering.py:963)
+// scratch layout (int64): [0..2047] digit histogram, [2048] prefix, [2049] rank (k),
+//                         [2050] n_pos, [2051] found bits of s[k], [2052] bits of s[k+1]
+// ------------------------------------------------------------------------------------------
+constexpr int SEL_BINS = 2048;
+
+__global__ void select_reset_kernel(long long* scratch) {
+    for (int i = threadIdx.x; i < SEL_BINS + 8; i += blockDim.x) scratch[i] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+select_count_kernel(const float* __restrict__ vals, long long n, long long* __restrict__ scratch) {
+    unsigned long long c = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        c += (__ldg(vals + i) > 0.0f) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd((unsigned long long*)&scratch[SEL_BINS + 2], c);
+}
+
+// pass p in {0,1,2}: digits are bits [21,32), [10,21), [0,10) of the (positive) float pattern
+__device__ __forceinline__ void digit_of(int pass, uint32_t u, uint32_t& dig, uint32_t& prefix_bits) {
+    if (pass == 0) { dig = u >> 21; prefix_bits = 0; }
+    else if (pass == 1) { dig = (u >> 10) & 0x7ffu; prefix_bits = u >> 21; }
+    else { dig = u & 0x3ffu; prefix_bits = u >> 10; }
+}
+
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const float* __restrict__ vals, long long n, int pass, int which,
+                   long long* __restrict__ scratch) {
+    __shared__ unsigned int local[SEL_BINS];
+    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x) local[i] = 0;
+    __syncthreads();
+    const uint32_t want = (uint32_t)scratch[SEL_BINS + 0];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float f = __ldg(vals + i);
+        if (!(f > 0.0f)) continue;
+        uint32_t dig, pre;
+        digit_of(pass, nb::f2u(f), dig, pre);
+        if (pass == 0 || pre == want) atomicAdd(&local[dig], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SEL_BINS; i += blockDim.x)
+        if (local[i]) atomicAdd((unsigned long long*)&scratch[i], (unsigned long long)local[i]);
+    (void)which;
+}
+
+// single thread: walk the digit histogram to locate rank k, update prefix / residual rank
+__global__ void select_scan_kernel(long long* scratch, int pass, int which) {
+    if (threadIdx.x != 0) return;
+    long long k = scratch[SEL_BINS + 1];
+    long long run = 0;
+    int d = 0;
+    const int nd = pass == 2 ? 1024 : 2048;
+    for (; d < nd; ++d) {
+        const long long c = scratch[d];
+        if (run + c > k) break;
+        run += c;
+    }
+    if (d >= nd) d = nd - 1;
+    const uint32_t prev = (uint32_t)scratch[SEL_BINS + 0];
+    uint32_t pre = pass == 0 ? (uint32_t)d : (pass == 1 ? ((prev << 11) | (uint32_t)d) : ((prev << 10) | (uint32_t)d));
+    scratch[SEL_BINS + 0] = (long long)pre;
+    scratch[SEL_BINS + 1] = k - run;
+    if (pass == 2) scratch[SEL_BINS + 3 + which] = (long long)pre;  // full 32-bit pattern
+    for (int i = 0; i < SEL_BINS; ++i) scratch[i] = 0;
+}
+
+__global__ void select_begin_kernel(long long* scratch, double q_percent, int which) {
+    if (threadIdx.x != 0) return;
+    // numpy 'linear': q = float32(q)/float32(100); virtual = (n-1)*q in float32; k = floor(virtual)
+    const long long n = scratch[SEL_BINS + 2];
+    const float q = (float)q_percent / 100.0f;
+    const float virt = (float)(n - 1) * q;
+    long long k = (long long)floorf(virt);
+    if (n > 0 && virt >= (float)(n - 1)) k = n - 1;     // _get_indexes: clamp to the last element
+    if (k < 0) k = 0;
+    long long kk = k + which;
+    if (kk > n - 1) kk = n - 1;
+    if (n > 0 && virt >= (float)(n - 1)) kk = n - 1;
+    scratch[SEL_BINS + 0] = 0;
+    scratch[SEL_BINS + 1] = kk;
+}
+
+__global__ void select_finish_kernel(const long long* scratch, double q_percent, double* out) {
+    if (threadIdx.x != 0) return;
+    const long long n = scratch[SEL_BINS + 2];
+    out[1] = (double)n;
+    if (n <= 0) { out[0] = 0.0; return; }
+    const float a = nb::u2f((uint32_t)scratch[SEL_BINS + 3]);
+    const float b = nb::u2f((uint32_t)scratch[SEL_BINS + 4]);
+    const float q = (float)q_percent / 100.0f;
+    const float virt = (float)(n - 1) * q;
+    float g = virt - floorf(virt);
+    if (virt >= (float)(n - 1)) g = 0.0f;  // previous == next == last
+    // numpy _lerp in float32
+    const float diff = b - a;
+    float res = a + diff * g;
+    if (g >= 0.5f) res = b - diff * (1.0f - g);
+    out[0] = (double)res;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int nb200_lattice_sample(const float* src, const nb200_vol* vol, int sz, int sy, int sx, float* out,
+                         void* stream) {
+    NB_REQUIRE(src && vol && out && sz > 0 && sy > 0 && sx > 0, NB200_ERR_ARG, "nb200_lattice_sample: bad argument");
+    const nb200_vol v = *vol;
+    const int g0 = v.zc0 + v.zg_off, g1 = v.zc1 + v.zg_off;
+    const int g_first = ((g0 + sz - 1) / sz) * sz;
+    const int n_lat_z = g_first < g1 ? (g1 - 1 - g_first) / sz + 1 : 0;
+    const int ly = (v.ny + sy - 1) / sy, lx = (v.nx + sx - 1) / sx;
+    const long long total = (long long)n_lat_z * ly * lx;
+    if (total == 0) return NB200_OK;
+    lattice_sample_kernel<<<nb::grid_for(total, 256, 8), 256, 0, nb::as_stream(stream)>>>(
+        src, v, sz, sy, sx, g_first, n_lat_z, ly, lx, out);
+    return nb::check_launch("lattice_sample");
+}
+
+int nb200_strided_sample(const float* src, long long n, long long offset, long long step, const float* gate,
+                         float gate_thresh, float* out, void* stream) {
+    NB_REQUIRE(src && out && step > 0 && offset >= 0, NB200_ERR_ARG, "nb200_strided_sample: bad argument");
+    const long long n_out = offset < n ? (n - offset + step - 1) / step : 0;
+    if (n_out == 0) return NB200_OK;
+    strided_sample_kernel<<<nb::grid_for(n_out, 256, 8), 256, 0, nb::as_stream(stream)>>>(
+        src, n_out, offset, step, gate, gate_thresh, out);
+    return nb::check_launch("strided_sample");
+}
+
+int nb200_hist_reset(long long* state, void* stream) {
+    NB_REQUIRE(state, NB200_ERR_ARG, "nb200_hist_reset: null state");
+    hist_reset_kernel<<<2, 256, 0, nb::as_stream(stream)>>>(state);
+    return nb::check_launch("hist_reset");
+}
+
+int nb200_hist_minmax(const float* vals, long long n, int transform, const double* divisor, long long* state,
+                      void* stream) {
+    NB_REQUIRE(vals && state && n >= 0, NB200_ERR_ARG, "nb200_hist_minmax: bad argument");
+    NB_REQUIRE(transform != NB200_TF_DIV || divisor, NB200_ERR_ARG, "nb200_hist_minmax: divisor required");
+    if (n == 0) return NB200_OK;
+    hist_minmax_kernel<<<nb::grid_for(n, 256, 4), 256, 0, nb::as_stream(stream)>>>(vals, n, transform, divisor, state);
+    return nb::check_launch("hist_minmax");
+}
+
+int nb200_hist_bins(const float* vals, long long n, int transform, const double* divisor, long long* state,
+                    void* stream) {
+    NB_REQUIRE(vals && state && n >= 0, NB200_ERR_ARG, "nb200_hist_bins: bad argument");
+    NB_REQUIRE(transform != NB200_TF_DIV || divisor, NB200_ERR_ARG, "nb200_hist_bins: divisor required");
+    if (n == 0) return NB200_OK;
+    hist_bins_kernel<<<nb::grid_for(n, 256, 4), 256, 0, nb::as_stream(stream)>>>(vals, n, transform, divisor, state);
+    return nb::check_launch("hist_bins");
+}
+
+int nb200_finalize_gamma(const long long* state, double* sp, void* stream) {
+    NB_REQUIRE(state && sp, NB200_ERR_ARG, "nb200_finalize_gamma: null argument");
+    finalize_gamma_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(state, sp);
+    return nb::check_launch("finalize_gamma");
+}
+
+int nb200_finalize_max_abs(const long long* hstats, double* sp, void* stream) {
+    NB_REQUIRE(hstats && sp, NB200_ERR_ARG, "nb200_finalize_max_abs: null argument");
+    finalize_max_abs_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(hstats, sp);
+    return nb::check_launch("finalize_max_abs");
+}
+
+int nb200_finalize_frob(const long long* state, const long long* hstats, double fixed_thresh, double division,
+                        double* sp, void* stream) {
+    NB_REQUIRE(state && hstats && sp, NB200_ERR_ARG, "nb200_finalize_frob: null argument");
+    finalize_frob_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(state, hstats, fixed_thresh, division, sp);
+    return nb::check_launch("finalize_frob");
+}
+
+int nb200_finalize_label_threshold(const long long* state, int log_domain, double* out, void* stream) {
+    NB_REQUIRE(state && out, NB200_ERR_ARG, "nb200_finalize_label_threshold: null argument");
+    finalize_label_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(state, log_domain, out);
+    return nb::check_launch("finalize_label_threshold");
+}
+
+int nb200_percentile(const float* samples, long long n, double q_percent, long long* scratch, double* out,
+                     void* stream) {
+    NB_REQUIRE(samples && scratch && out && n >= 0, NB200_ERR_ARG, "nb200_percentile: bad argument");
+    cudaStream_t st = nb::as_stream(stream);
+    select_reset_kernel<<<1, 256, 0, st>>>(scratch);
+    if (n > 0) select_count_kernel<<<nb::grid_for(n, 256, 4), 256, 0, st>>>(samples, n, scratch);
+    for (int which = 0; which < 2; ++which) {
+        select_begin_kernel<<<1, 32, 0, st>>>(scratch, q_percent, which);
+        for (int pass = 0; pass < 3 && n > 0; ++pass) {
+            select_hist_kernel<<<nb::grid_for(n, 256, 2), 256, 0, st>>>(samples, n, pass, which, scratch);
+            select_scan_kernel<<<1, 32, 0, st>>>(scratch, pass, which);
+        }
+    }
+    select_finish_kernel<<<1, 32, 0, st>>>(scratch, q_percent, out);
+    return nb::check_launch("percentile");
+}
+
+}  // extern "C"

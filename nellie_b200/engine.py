@@ -1,0 +1,303 @@
+"""Device-side orchestration of one frame of the Filter hot path (single GPU or one Z slab).
+
+Everything here is plumbing: torch owns the device buffers and the stream, every arithmetic
+step is a kernel of ``libnellie_b200.so`` called through the C ABI, and no scalar comes back to
+the host inside a frame (gamma, thresholds and max|H| stay in the device record ``sp``).
+
+Reference control flow restated: nellie/segmentation/filtering.py:806-853 (_compute_vesselness),
+:910-933 (_run_frame), :952-967 (_mask_volume), :1005-1031 (_run_filter).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import Vol
+
+
+# ---------------------------------------------------------------------------------------------
+# host-side scalar logic (F0): sigma schedule, spacing, sampling strides, Gaussian taps
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class FilterParams:
+    """Constructor knobs of the reference Filter (filtering.py:23-40) plus the physical pixel sizes."""
+    dim_res: dict
+    no_z: bool = False
+    min_radius_um: float = 0.25
+    max_radius_um: float = 1.0
+    alpha_sq: float = 0.5
+    beta_sq: float = 0.5
+    frob_thresh: Optional[float] = None
+    frob_thresh_division: float = 2
+    max_threshold_samples: int = 1_000_000
+    truncate: float = 3.0
+    remove_edges: bool = False
+    sigmas: Optional[Sequence[float]] = None
+
+    def z_ratio(self) -> float:  # filtering.py:75-78
+        z_res = self.dim_res.get("Z") or self.dim_res.get("X") or 1.0
+        x_res = self.dim_res.get("X") or 1.0
+        return float(z_res) / float(x_res)
+
+    def spacing(self):  # filtering.py:265-275
+        y = float(self.dim_res.get("Y") or 1.0)
+        x = float(self.dim_res.get("X") or 1.0)
+        if self.no_z:
+            return (y, x)
+        z = float(self.dim_res.get("Z") or self.dim_res.get("X") or 1.0)
+        return (z, y, x)
+
+    def sigma_list(self):  # filtering.py:288-316
+        if self.sigmas is not None:
+            return sorted(float(s) for s in self.sigmas)
+        lo_px = self.min_radius_um / self.dim_res["X"]
+        hi_px = self.max_radius_um / self.dim_res["X"]
+        a, b = lo_px / 2.0, hi_px / 3.0
+        s_min, s_max = min(a, b), max(a, b)
+        if s_max <= s_min:
+            s_max = s_min + 0.2
+        step = max(0.2, (s_max - s_min) / 5.0)
+        vals = list(np.arange(s_min, s_max, step, dtype=float))
+        vals.sort()
+        return [float(v) for v in vals]
+
+    def sigma_vec(self, sigma):  # filtering.py:277-286
+        if self.no_z:
+            return (float(sigma), float(sigma))
+        return (float(sigma) / self.z_ratio(), float(sigma), float(sigma))
+
+    def delta_sigma_vec(self, prev, cur):  # filtering.py:816-825
+        return tuple(float(np.sqrt(max(0.0, float(c) ** 2 - float(p) ** 2)))
+                     for p, c in zip(self.sigma_vec(prev), self.sigma_vec(cur)))
+
+    def fd_spacing_f32(self):
+        """[fl32(h), fl32(2h)] per axis: numpy.gradient divides a float32 array by the Python floats
+        ``h`` (edges) and ``2. * h`` (interior), both cast to float32."""
+        out = []
+        for h in self.spacing():
+            out += [np.float32(h), np.float32(2.0 * h)]
+        return np.asarray(out, dtype=np.float32)
+
+
+def sample_strides(shape, max_samples):
+    """filtering.py:328-340 (_sample_strides)."""
+    nd = len(shape)
+    if max_samples is None or max_samples <= 0:
+        return (1,) * nd
+    total = int(np.prod(shape))
+    if total <= max_samples:
+        return (1,) * nd
+    s0 = max(1, int(np.ceil((total / max_samples) ** (1.0 / nd))))
+    st = [s0] * nd
+    while int(np.prod([int(np.ceil(n / s)) for n, s in zip(shape, st)])) > max_samples:
+        k = int(np.argmax([n / s for n, s in zip(shape, st)]))
+        st[k] += 1
+    return tuple(st)
+
+
+def gaussian_taps(delta_sigma: float, truncate: float):
+    """scipy.ndimage._gaussian_kernel1d(order=0): radius int(truncate*sd+0.5); returns (w[0..r], r)."""
+    sd = float(delta_sigma)
+    radius = int(truncate * sd + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+    phi = phi / phi.sum()
+    return np.ascontiguousarray(phi[radius:], dtype=np.float64), radius
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------
+# 3-D engine
+# ---------------------------------------------------------------------------------------------
+class FrangiEngine3D:
+    """Buffers + kernel sequence for frames of one shape ``(nz, ny, nx)`` on one GPU.
+
+    ``slab`` describes a Z slab of a larger frame for multi-GPU runs (see sharding.py); by default the
+    engine owns the whole frame.  Buffers: two blurred volumes (ping-pong), the accumulator and the
+    output — 16 B/voxel resident, 8 GiB... 16 GiB for a 1024^3 frame, well inside 180 GB of HBM3e.
+    """
+
+    def __init__(self, shape, params: FilterParams, device=None, slab=None):
+        if params.no_z or len(shape) != 3:
+            raise ValueError("FrangiEngine3D needs a (Z, Y, X) frame")
+        self.p = params
+        self.device = torch.device(device if device is not None else "cuda")
+        self.lib = _cabi.load()
+        self.sigmas = params.sigma_list()
+        self.steps = []
+        prev = 0.0
+        for s in self.sigmas:
+            dvec = params.delta_sigma_vec(prev, s)
+            taps = [gaussian_taps(d, params.truncate) if d > 1e-15 else None for d in dvec]
+            self.steps.append(taps)
+            prev = s
+        self.halo_z = 2 + max([t[0][1] for t in self.steps if t[0] is not None] + [0])
+        # slab geometry --------------------------------------------------------------------
+        if slab is None:
+            nz, ny, nx = (int(s) for s in shape)
+            self.nz_glob, self.z0, self.nz_own = nz, 0, nz
+        else:
+            self.nz_glob, self.z0, self.nz_own = slab
+            ny, nx = int(shape[-2]), int(shape[-1])
+        self.ny, self.nx = ny, nx
+        self.pad_lo = min(self.halo_z, self.z0)
+        self.pad_hi = min(self.halo_z, self.nz_glob - (self.z0 + self.nz_own))
+        self.nz_buf = self.pad_lo + self.nz_own + self.pad_hi
+        self.zg_off = self.z0 - self.pad_lo
+        if min(self.nz_glob, ny, nx) < 2:
+            raise ValueError("numpy.gradient needs at least 2 samples along every axis")
+        self.strides = sample_strides((self.nz_glob, ny, nx), params.max_threshold_samples)
+        sz, sy, sx = self.strides
+        g0, g1 = self.z0, self.z0 + self.nz_own
+        first = ((g0 + sz - 1) // sz) * sz
+        self.n_lat_z = (g1 - 1 - first) // sz + 1 if first < g1 else 0
+        self.n_samples = self.n_lat_z * math.ceil(ny / sy) * math.ceil(nx / sx)
+        dev = self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.gauss = [torch.empty((self.nz_buf, ny, nx), **f32) for _ in range(2)]
+        self.acc = torch.empty((self.nz_buf, ny, nx), **f32)
+        self.out = torch.empty((self.nz_own, ny, nx), **f32)
+        self.samples = torch.empty(max(1, self.n_samples), **f32)
+        self.hist = torch.zeros(_cabi.HIST_WORDS, dtype=torch.int64, device=dev)
+        self.hstats = torch.zeros(_cabi.HS_WORDS, dtype=torch.int64, device=dev)
+        self.sp = torch.zeros((len(self.sigmas), _cabi.SP_WORDS), dtype=torch.float64, device=dev)
+        self.select = torch.zeros(_cabi.SELECT_WORDS, dtype=torch.int64, device=dev)
+        self.pct = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.fd = params.fd_spacing_f32()
+        self._fd_c = self.fd.ctypes.data_as(C.POINTER(C.c_float))
+        self.launches = 0
+        # hooks for the multi-GPU driver (identity on one GPU)
+        self.exchange_halo = lambda buf, depth: None
+        self.reduce_hist_minmax = lambda state: None
+        self.reduce_hist_bins = lambda state: None
+        self.reduce_hstats = lambda hs: None
+        self.gather_samples = lambda s, n: (s, n)
+
+    # -- geometry helpers ---------------------------------------------------------------------
+    def vol(self, extra_lo=0, extra_hi=0) -> Vol:
+        """Window over the owned planes, optionally widened into the halo (clipped at the frame)."""
+        zc0 = self.pad_lo - min(extra_lo, self.pad_lo)
+        zc1 = self.pad_lo + self.nz_own + min(extra_hi, self.pad_hi)
+        return Vol(self.nz_buf, self.ny, self.nx, zc0, zc1, self.zg_off, self.nz_glob)
+
+    def _call(self, name, *args):
+        self.launches += 1
+        _cabi.check(getattr(self.lib, name)(*args), name)
+
+    # -- thresholds from a sample buffer --------------------------------------------------------
+    def _histogram(self, samples, n, transform, divisor_ptr):
+        st = _stream()
+        self._call("nb200_hist_reset", _ptr(self.hist), st)
+        self._call("nb200_hist_minmax", _ptr(samples), n, transform, divisor_ptr, _ptr(self.hist), st)
+        self.reduce_hist_minmax(self.hist)
+        self._call("nb200_hist_bins", _ptr(samples), n, transform, divisor_ptr, _ptr(self.hist), st)
+        self.reduce_hist_bins(self.hist)
+
+    # -- one frame ----------------------------------------------------------------------------
+    def load_frame(self, frame: torch.Tensor):
+        """Copy the owned planes of ``frame`` (any real dtype, device tensor) into the blur buffer as
+        float32 (filtering.py:924: xp.asarray(frame, dtype=float32)); the caller's tensor is never
+        written (the reference aliases and overwrites float32 inputs — SURVEY App. C-1)."""
+        own = self.gauss[0][self.pad_lo:self.pad_lo + self.nz_own]
+        own.copy_(frame)
+        self.cur = 0
+
+    def run_sigmas(self):
+        """filtering.py:814-851 for every sigma; leaves max-over-sigma / dead flags in ``acc``."""
+        st = _stream()
+        self.acc.zero_()
+        sz, sy, sx = self.strides
+        for i, taps in enumerate(self.steps):
+            sp_i = self.sp[i]
+            # F1: incremental blur, axes Z, Y, X in order (scipy processes axes 0,1,2)
+            if any(t is not None for t in taps):
+                rz = taps[0][1] if taps[0] is not None else 0
+                self.exchange_halo(self.gauss[self.cur], rz + 2)
+                for axis, t in enumerate(taps):
+                    if t is None or t[1] == 0:
+                        continue
+                    w, r = t
+                    src, dst = self.gauss[self.cur], self.gauss[1 - self.cur]
+                    # Z pass over owned+2 planes (reads the exchanged halo); Y/X passes likewise so the
+                    # Hessian stencil finds blurred neighbours without a second exchange
+                    v = self.vol(2, 2)
+                    self._call("nb200_gauss_axis", _ptr(src), _ptr(dst), C.byref(v), axis,
+                               w.ctypes.data_as(C.POINTER(C.c_double)), r, st)
+                    self.cur = 1 - self.cur
+            g = self.gauss[self.cur]
+            own = self.vol()
+            # F2/F3: gamma from the positive lattice sample of the blurred volume
+            self._call("nb200_lattice_sample", _ptr(g), C.byref(own), sz, sy, sx, _ptr(self.samples), st)
+            self._histogram(self.samples, self.n_samples, _cabi.TF_NONE, None)
+            self._call("nb200_finalize_gamma", _ptr(self.hist), _ptr(sp_i), st)
+            # F4: Hessian statistics (max|H|, max frob^2, frob samples)
+            self._call("nb200_hstats_reset", _ptr(self.hstats), st)
+            self._call("nb200_hessian_stats", _ptr(g), C.byref(own), self._fd_c, sz, sy, sx,
+                       _ptr(self.samples), _ptr(self.hstats), st)
+            self.reduce_hstats(self.hstats)
+            self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
+            # F5: Frobenius threshold
+            fixed = float("nan") if self.p.frob_thresh is None else float(self.p.frob_thresh)
+            division = float(self.p.frob_thresh_division or 0.0)
+            if self.p.frob_thresh is None and division != 0.0:
+                div_ptr = C.c_void_p(sp_i.data_ptr() + 8 * _cabi.SP_MAX_ABS)
+                self._histogram(self.samples, self.n_samples, _cabi.TF_DIV, div_ptr)
+            else:
+                self._call("nb200_hist_reset", _ptr(self.hist), st)
+            self._call("nb200_finalize_frob", _ptr(self.hist), _ptr(self.hstats), fixed, division, _ptr(sp_i), st)
+            # F4-F9 fused
+            self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c,
+                       float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
+
+    def finalize(self, apply_mask_volume=True):
+        """filtering.py:926 (V*masks) + :1014-1018 / :952-967 (_mask_volume)."""
+        st = _stream()
+        own = self.vol()
+        sz, sy, sx = self.strides
+        if apply_mask_volume:
+            self._call("nb200_lattice_sample", _ptr(self.acc), C.byref(own), sz, sy, sx, _ptr(self.samples), st)
+            samples, n = self.gather_samples(self.samples, self.n_samples)
+            self._call("nb200_percentile", _ptr(samples), n, 1.0, _ptr(self.select), _ptr(self.pct), st)
+        else:
+            self.pct.zero_()   # pct[1] == 0 -> pass-through
+        self.exchange_halo(self.acc, 2)
+        # output is written for the owned planes only; give the kernel a view whose plane 0 is buffer plane 0
+        out_full = self.out if self.nz_buf == self.nz_own else None
+        if out_full is None:
+            if not hasattr(self, "_out_buf"):
+                self._out_buf = torch.empty_like(self.acc)
+            self._call("nb200_finalize_opening", _ptr(self.acc), _ptr(self._out_buf), C.byref(own), _ptr(self.pct), st)
+            self.out.copy_(self._out_buf[self.pad_lo:self.pad_lo + self.nz_own])
+        else:
+            self._call("nb200_finalize_opening", _ptr(self.acc), _ptr(self.out), C.byref(own), _ptr(self.pct), st)
+        return self.out
+
+    def filter_frame(self, frame: torch.Tensor, apply_mask_volume=True) -> torch.Tensor:
+        """Device tensor in, device tensor out (the engine's own output buffer)."""
+        if self.p.remove_edges:
+            raise NotImplementedError("remove_edges (filtering.py:969-1000) is not implemented on the B200 path yet")
+        self.load_frame(frame)
+        self.run_sigmas()
+        return self.finalize(apply_mask_volume)
+
+    def mask_volume(self, v: torch.Tensor) -> torch.Tensor:
+        """_mask_volume (filtering.py:952-967) of an already computed response ``v`` (>= 0)."""
+        self.acc[self.pad_lo:self.pad_lo + self.nz_own].copy_(v)
+        return self.finalize(True)
+
+    def sigma_records(self):
+        """Per-sigma device scalars copied to the host (tests / diagnostics; forces a sync)."""
+        return self.sp.cpu().numpy()
