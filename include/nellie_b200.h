@@ -156,6 +156,22 @@ int nb200_percentile(const float* samples, long long n, double q_percent, long l
 int nb200_finalize_opening(const float* acc, float* out, const nb200_vol* vol, const double* thr, void* stream);
 int nb200_finalize_opening_2d(const float* v, float* out, int ny, int nx, const double* thr, void* stream);
 
+/* ---- L4/L5: Label._get_labels (labelling.py:467-509, :546-556) -------------------------------
+ * threshold (strict >, optional intensity gate on `raw`) -> fill holes (3-D only) -> 26-/8-connected
+ * components -> drop components smaller than min_area -> 3^d majority smoothing -> components again.
+ * labels: int32, 0 = background, ids 1..n in raster order of each component's first voxel
+ * (scipy.ndimage.label numbering).  thr: device double[5] as written by
+ * nb200_finalize_label_threshold (thr[0] = threshold, thr[3] != 0 -> "None": empty mask).
+ * nz = 1 selects the 2-D path.  workspace: nb200_label_workspace_bytes() bytes of device memory.
+ * n_labels: device int64 receiving the component count. */
+size_t nb200_label_workspace_bytes(int nz, int ny, int nx);
+int nb200_label_frame(const float* frangi, const float* raw, int use_intensity, float intensity_thresh,
+                      const double* thr, int nz, int ny, int nx, long long min_area, int fill_holes,
+                      int* labels, void* workspace, long long* n_labels, void* stream);
+/* scipy.ndimage.label alone on a uint8 mask; connectivity_full: 1 = 26/8-connected, 0 = 6/4. */
+int nb200_ccl_label(const unsigned char* mask, int nz, int ny, int nx, int connectivity_full, int* labels,
+                    void* workspace, long long* n_labels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

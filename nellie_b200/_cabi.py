@@ -62,6 +62,10 @@ _SIGS = {
     "nb200_percentile": ([_p, _ll, C.c_double, _p, _p, _p], C.c_int),
     "nb200_finalize_opening": ([_p, _p, C.POINTER(Vol), _p, _p], C.c_int),
     "nb200_finalize_opening_2d": ([_p, _p, C.c_int, C.c_int, _p, _p], C.c_int),
+    "nb200_label_workspace_bytes": ([C.c_int, C.c_int, C.c_int], C.c_size_t),
+    "nb200_label_frame": ([_p, _p, C.c_int, C.c_float, _p, C.c_int, C.c_int, C.c_int, _ll, C.c_int, _p, _p, _p, _p],
+                          C.c_int),
+    "nb200_ccl_label": ([_p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p], C.c_int),
 }
 
 _lib = None

@@ -1,0 +1,425 @@
+// L4/L5 — Label._get_labels on device (nellie/segmentation/labelling.py:467-509, :546-556):
+//   mask = (frangi * (raw > intensity_thr)) > frangi_thr          (strict, float32)
+//   3-D: mask = binary_fill_holes(mask)       = fg | background components not 6-connected to the border
+//   labels = label(mask, ones(3,3[,3]))       26-/8-connectivity
+//   drop components with fewer than min_area voxels
+//   mask = uniform_filter(float32(mask), 3, mode="reflect") > 0.5   = (set voxels in the reflected 3^d window) >= 14 (5 in 2-D)
+//   labels = label(mask) : int32, ids 1..n in raster order of each component's first voxel (scipy.ndimage.label)
+//
+// Connected components: union-find over voxel indices in global memory.  X-runs are pre-linked
+// with warp ballots (every voxel starts pointing at the first voxel of its run inside a 32-wide
+// window), so only run heads ever take part in atomics; unions always hang the larger root under
+// the smaller one (atomicMin), so a component's root is its first voxel in raster order and
+// scipy's numbering is reproduced by ranking the roots.  Background components for fill-holes use
+// a virtual "outside" root (-2) that every border voxel links to.
+//
+// Integer / byte work: the bound is HBM traffic (frangi read + int32 labels write = 8 B/voxel
+// algorithmic; the parent array and the byte masks are honest extra traffic).
+#include "common.cuh"
+
+namespace {
+
+constexpr int OUTSIDE = -2;
+constexpr int NOT_IN_SET = -1;
+constexpr int THREADS = 256;
+
+struct Dims {
+    int nz, ny, nx;
+    long long plane, total;
+};
+
+__device__ __forceinline__ int ld_parent(const int* parent, long long i) {
+    return *reinterpret_cast<const volatile int*>(parent + i);
+}
+
+__device__ __forceinline__ int find_root(int* parent, int x) {
+    int p = ld_parent(parent, x);
+    while (p != x && p >= 0) {
+        const int gp = ld_parent(parent, p);
+        if (gp != p) parent[x] = gp;  // path halving; ancestors stay ancestors, so stale writes are harmless
+        x = p;
+        p = gp;
+    }
+    return p;  // own index for a root, OUTSIDE for a border-connected background tree
+}
+
+__device__ __forceinline__ void unite(int* parent, int a, int b) {
+    while (true) {
+        a = find_root(parent, a);
+        b = find_root(parent, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }   // a > b, b may be OUTSIDE
+        const int old = atomicMin(parent + a, b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__device__ __forceinline__ void link_outside(int* parent, int a) {
+    while (true) {
+        a = find_root(parent, a);
+        if (a < 0) return;
+        const int old = atomicMin(parent + a, OUTSIDE);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// ---- threshold ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS)
+threshold_mask_kernel(const float* __restrict__ frangi, const float* __restrict__ raw, int use_intensity,
+                      float intensity_thresh, const double* __restrict__ thr, long long n,
+                      unsigned char* __restrict__ mask) {
+    const bool none = thr[3] != 0.0;            // no samples: mask = zeros (labelling.py:475-476)
+    const float cut = (float)thr[0];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float f = __ldg(frangi + i);
+        if (use_intensity) f = f * ((__ldg(raw + i) > intensity_thresh) ? 1.0f : 0.0f);   // labelling.py:550-552
+        mask[i] = (!none && f > cut) ? 1 : 0;
+    }
+}
+
+// ---- CCL ---------------------------------------------------------------------------------------
+// `want` selects the set: voxels with mask == want are in the set.
+__global__ void __launch_bounds__(THREADS)
+ccl_init_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims d, int* __restrict__ parent) {
+    // one warp per 32-wide x window; windows per row = ceil(nx/32)
+    const int wpr = (d.nx + 31) / 32;
+    const long long nwin = (long long)d.nz * d.ny * wpr;
+    const int lane = threadIdx.x & 31;
+    for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < nwin;
+         w += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const long long row = w / wpr;
+        const int x = (int)(w - row * wpr) * 32 + lane;
+        const long long idx = row * d.nx + x;
+        const bool in = x < d.nx && mask[idx] == want;
+        const unsigned bits = __ballot_sync(0xffffffffu, in);
+        if (x < d.nx) {
+            int val = NOT_IN_SET;
+            if (in) {
+                const unsigned below_zero = ~bits & ((1u << lane) - 1u);
+                const int start = below_zero ? 32 - __clz(below_zero) : 0;
+                val = (int)(idx - lane + start);
+            }
+            parent[idx] = val;
+        }
+    }
+}
+
+template <bool FULL_CONN, bool BORDER_OUTSIDE>
+__global__ void __launch_bounds__(THREADS)
+ccl_merge_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims d, int* __restrict__ parent) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
+         i += (long long)gridDim.x * blockDim.x) {
+        if (mask[i] != want) continue;
+        const int z = (int)(i / d.plane);
+        const long long rem = i - (long long)z * d.plane;
+        const int y = (int)(rem / d.nx), x = (int)(rem - (long long)y * d.nx);
+        const int me = (int)i;
+        auto in = [&](int dz, int dy, int dx) -> bool {
+            const int zz = z + dz, yy = y + dy, xx = x + dx;
+            if (zz < 0 || yy < 0 || yy >= d.ny || xx < 0 || xx >= d.nx) return false;
+            return mask[i + (long long)dz * d.plane + (long long)dy * d.nx + dx] == want;
+        };
+        auto off = [&](int dz, int dy, int dx) -> int {
+            return (int)(i + (long long)dz * d.plane + (long long)dy * d.nx + dx);
+        };
+        const bool w_in = in(0, 0, -1);
+        if (w_in && (x & 31) == 0) unite(parent, me, me - 1);      // stitch 32-wide windows of one run
+        if (!FULL_CONN) {
+            // 6-/4-connectivity: link to the row above / plane above once per overlap of two runs
+            if (in(0, -1, 0) && !(w_in && in(0, -1, -1))) unite(parent, me, off(0, -1, 0));
+            if (in(-1, 0, 0) && !(w_in && in(-1, 0, -1))) unite(parent, me, off(-1, 0, 0));
+        } else {
+            // 26-/8-connectivity, backward half.  A set centre neighbour already ties its whole
+            // row / plane together through those voxels' own links, so it stands for the rest.
+            if (in(0, -1, 0)) unite(parent, me, off(0, -1, 0));
+            else {
+                if (in(0, -1, -1)) unite(parent, me, off(0, -1, -1));
+                if (in(0, -1, 1)) unite(parent, me, off(0, -1, 1));
+            }
+            if (z > 0) {
+                if (in(-1, 0, 0)) unite(parent, me, off(-1, 0, 0));
+                else {
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx)
+                            if ((dy != 0 || dx != 0) && in(-1, dy, dx)) unite(parent, me, off(-1, dy, dx));
+                }
+            }
+        }
+        if (BORDER_OUTSIDE) {
+            const bool edge = z == 0 || z == d.nz - 1 || y == 0 || y == d.ny - 1 || x == 0 || x == d.nx - 1;
+            if (edge) link_outside(parent, me);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+ccl_flatten_kernel(Dims d, int* __restrict__ parent) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
+         i += (long long)gridDim.x * blockDim.x) {
+        if (parent[i] == NOT_IN_SET) continue;
+        const int r = find_root(parent, (int)i);
+        parent[i] = r;
+    }
+}
+
+// ---- fill holes: mask |= background voxels whose tree is not tied to OUTSIDE ----------------------
+__global__ void __launch_bounds__(THREADS)
+fill_holes_kernel(Dims d, const int* __restrict__ parent, unsigned char* __restrict__ mask) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int p = parent[i];            // flattened: root index, OUTSIDE, or NOT_IN_SET (foreground)
+        if (p >= 0) mask[i] = 1;
+    }
+}
+
+// ---- component sizes -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS)
+area_count_kernel(Dims d, const int* __restrict__ parent, int* __restrict__ area) {
+    for (long long base = blockIdx.x * (long long)blockDim.x; base < d.total; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;
+        const int r = i < d.total ? parent[i] : NOT_IN_SET;
+        const unsigned active = __ballot_sync(0xffffffffu, r >= 0);
+        if (r >= 0) {
+            const unsigned peers = __match_any_sync(active, r);
+            if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(area + r, __popc(peers));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+area_keep_kernel(Dims d, const int* __restrict__ parent, const int* __restrict__ area, long long min_area,
+                 unsigned char* __restrict__ keep) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = parent[i];
+        keep[i] = (r >= 0 && (long long)area[r] >= min_area) ? 1 : 0;
+    }
+}
+
+// ---- 3^d majority with reflected borders -----------------------------------------------------------
+__global__ void __launch_bounds__(THREADS)
+majority_kernel(const unsigned char* __restrict__ in, Dims d, unsigned char* __restrict__ out) {
+    const int need = d.nz > 1 ? 14 : 5;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(i / d.plane);
+        const long long rem = i - (long long)z * d.plane;
+        const int y = (int)(rem / d.nx), x = (int)(rem - (long long)y * d.nx);
+        int cnt = 0;
+        const int dz0 = d.nz > 1 ? -1 : 0, dz1 = d.nz > 1 ? 1 : 0;
+        for (int dz = dz0; dz <= dz1; ++dz) {
+            const int zz = min(max(z + dz, 0), d.nz - 1);      // reflect of a 1-voxel overhang = clamp
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int yy = min(max(y + dy, 0), d.ny - 1);
+                const unsigned char* row = in + (long long)zz * d.plane + (long long)yy * d.nx;
+                cnt += row[max(x - 1, 0)] + row[x] + row[min(x + 1, d.nx - 1)];
+            }
+        }
+        out[i] = cnt >= need ? 1 : 0;
+    }
+}
+
+// ---- raster-order numbering of the roots -------------------------------------------------------------
+constexpr int RANK_CHUNK = 2048;    // voxels per block in the counting / assigning kernels
+
+__global__ void __launch_bounds__(THREADS)
+root_count_kernel(Dims d, const int* __restrict__ parent, int* __restrict__ block_counts) {
+    __shared__ int warp_sums[THREADS / 32];
+    const long long base = (long long)blockIdx.x * RANK_CHUNK;
+    int c = 0;
+    for (int k = threadIdx.x; k < RANK_CHUNK; k += THREADS) {
+        const long long i = base + k;
+        if (i < d.total && parent[i] == (int)i) ++c;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int k = 0; k < THREADS / 32; ++k) s += warp_sums[k];
+        block_counts[blockIdx.x] = s;
+    }
+}
+
+// single CTA: exclusive scan of block_counts in place; total -> *n_labels
+__global__ void __launch_bounds__(1024)
+block_scan_kernel(int* __restrict__ block_counts, long long nblocks, long long* __restrict__ n_labels) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (long long base = 0; base < nblocks; base += 1024) {
+        const long long i = base + threadIdx.x;
+        const int v = i < nblocks ? block_counts[i] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_tot[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int t = warp_tot[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += u;
+            }
+            warp_tot[lane] = t;   // inclusive totals per warp
+        }
+        __syncthreads();
+        const int carry = carry_s;
+        const int before = (w ? warp_tot[w - 1] : 0) + carry;
+        if (i < nblocks) block_counts[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_labels = (long long)carry_s;
+}
+
+__global__ void __launch_bounds__(THREADS)
+root_assign_kernel(Dims d, const int* __restrict__ parent, const int* __restrict__ block_offsets,
+                   int* __restrict__ labels) {
+    // ranks inside a chunk follow raster order: the chunk is scanned in THREADS-wide strips
+    __shared__ int warp_sums[THREADS / 32];
+    __shared__ int running;
+    if (threadIdx.x == 0) running = block_offsets[blockIdx.x];
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * RANK_CHUNK;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int k0 = 0; k0 < RANK_CHUNK; k0 += THREADS) {
+        const long long i = base + k0 + threadIdx.x;
+        const bool is_root = i < d.total && parent[i] == (int)i;
+        const unsigned bits = __ballot_sync(0xffffffffu, is_root);
+        const int before_in_warp = __popc(bits & ((1u << lane) - 1u));
+        if (lane == 0) warp_sums[w] = __popc(bits);
+        __syncthreads();
+        int before = running;
+        for (int k = 0; k < w; ++k) before += warp_sums[k];
+        if (is_root) labels[i] = before + before_in_warp + 1;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int s = 0;
+            for (int k = 0; k < THREADS / 32; ++k) s += warp_sums[k];
+            running += s;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+label_propagate_kernel(Dims d, const int* __restrict__ parent, int* __restrict__ labels) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = parent[i];
+        if (r < 0) labels[i] = 0;
+        else if (r != (int)i) labels[i] = labels[r];
+    }
+}
+
+Dims make_dims(int nz, int ny, int nx) {
+    Dims d;
+    d.nz = nz; d.ny = ny; d.nx = nx;
+    d.plane = (long long)ny * nx;
+    d.total = d.plane * nz;
+    return d;
+}
+
+unsigned gs(long long n) { return nb::grid_for(n, THREADS, 8); }
+
+int run_ccl(const unsigned char* mask, unsigned char want, const Dims& d, bool full_conn, bool border_outside,
+            int* parent, cudaStream_t st) {
+    ccl_init_kernel<<<gs(d.total), THREADS, 0, st>>>(mask, want, d, parent);
+    if (full_conn && !border_outside) ccl_merge_kernel<true, false><<<gs(d.total), THREADS, 0, st>>>(mask, want, d, parent);
+    else if (!full_conn && border_outside) ccl_merge_kernel<false, true><<<gs(d.total), THREADS, 0, st>>>(mask, want, d, parent);
+    else if (!full_conn) ccl_merge_kernel<false, false><<<gs(d.total), THREADS, 0, st>>>(mask, want, d, parent);
+    else ccl_merge_kernel<true, true><<<gs(d.total), THREADS, 0, st>>>(mask, want, d, parent);
+    ccl_flatten_kernel<<<gs(d.total), THREADS, 0, st>>>(d, parent);
+    return nb::check_launch("ccl");
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t nb200_label_workspace_bytes(int nz, int ny, int nx) {
+    const long long n = (long long)nz * ny * nx;
+    const long long nblocks = (n + RANK_CHUNK - 1) / RANK_CHUNK;
+    // parent int32[n] | mask_a u8[n] | mask_b u8[n] | block counts int32[nblocks] (each 256-byte aligned)
+    auto al = [](long long b) { return (b + 255) / 256 * 256; };
+    return (size_t)(al(4 * n) + al(n) + al(n) + al(4 * nblocks));
+}
+
+int nb200_label_frame(const float* frangi, const float* raw, int use_intensity, float intensity_thresh,
+                      const double* thr, int nz, int ny, int nx, long long min_area, int fill_holes,
+                      int* labels, void* workspace, long long* n_labels, void* stream) {
+    NB_REQUIRE(frangi && thr && labels && workspace && n_labels, NB200_ERR_ARG, "nb200_label_frame: null argument");
+    NB_REQUIRE(!use_intensity || raw, NB200_ERR_ARG, "nb200_label_frame: raw frame required for intensity gating");
+    NB_REQUIRE(nz >= 1 && ny >= 1 && nx >= 1, NB200_ERR_ARG, "nb200_label_frame: bad shape");
+    const long long n = (long long)nz * ny * nx;
+    NB_REQUIRE(n < 2147483000LL, NB200_ERR_UNSUPPORTED, "nb200_label_frame: frame exceeds int32 voxel indexing");
+    const Dims d = make_dims(nz, ny, nx);
+    cudaStream_t st = nb::as_stream(stream);
+    auto al = [](long long b) { return (b + 255) / 256 * 256; };
+    char* ws = static_cast<char*>(workspace);
+    int* parent = reinterpret_cast<int*>(ws);
+    unsigned char* mask_a = reinterpret_cast<unsigned char*>(ws + al(4 * n));
+    unsigned char* mask_b = mask_a + al(n);
+    int* block_counts = reinterpret_cast<int*>(mask_b + al(n));
+    const long long nblocks = (n + RANK_CHUNK - 1) / RANK_CHUNK;
+    int rc;
+
+    threshold_mask_kernel<<<gs(n), THREADS, 0, st>>>(frangi, raw, use_intensity, intensity_thresh, thr, n, mask_a);
+    if (fill_holes && nz > 1) {   // labelling.py:485-486 (3-D only)
+        rc = run_ccl(mask_a, 0, d, /*full_conn=*/false, /*border_outside=*/true, parent, st);
+        if (rc) return rc;
+        fill_holes_kernel<<<gs(n), THREADS, 0, st>>>(d, parent, mask_a);
+    }
+    // first labelling + size filter (labelling.py:489-501)
+    rc = run_ccl(mask_a, 1, d, true, false, parent, st);
+    if (rc) return rc;
+    cudaMemsetAsync(labels, 0, sizeof(int) * n, st);
+    area_count_kernel<<<gs(n), THREADS, 0, st>>>(d, parent, labels);
+    area_keep_kernel<<<gs(n), THREADS, 0, st>>>(d, parent, labels, min_area, mask_b);
+    // smoothing (labelling.py:503-505) and second labelling (:507)
+    majority_kernel<<<gs(n), THREADS, 0, st>>>(mask_b, d, mask_a);
+    rc = run_ccl(mask_a, 1, d, true, false, parent, st);
+    if (rc) return rc;
+    root_count_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(d, parent, block_counts);
+    block_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, n_labels);
+    root_assign_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(d, parent, block_counts, labels);
+    label_propagate_kernel<<<gs(n), THREADS, 0, st>>>(d, parent, labels);
+    return nb::check_launch("label_frame");
+}
+
+/* scipy.ndimage.label(mask, structure=ones) alone (used by tests and by the Network stage later):
+ * mask: uint8 device array; connectivity_full: 1 = 26/8, 0 = 6/4. */
+int nb200_ccl_label(const unsigned char* mask, int nz, int ny, int nx, int connectivity_full, int* labels,
+                    void* workspace, long long* n_labels, void* stream) {
+    NB_REQUIRE(mask && labels && workspace && n_labels, NB200_ERR_ARG, "nb200_ccl_label: null argument");
+    const long long n = (long long)nz * ny * nx;
+    NB_REQUIRE(n < 2147483000LL, NB200_ERR_UNSUPPORTED, "nb200_ccl_label: frame exceeds int32 voxel indexing");
+    const Dims d = make_dims(nz, ny, nx);
+    cudaStream_t st = nb::as_stream(stream);
+    auto al = [](long long b) { return (b + 255) / 256 * 256; };
+    char* ws = static_cast<char*>(workspace);
+    int* parent = reinterpret_cast<int*>(ws);
+    int* block_counts = reinterpret_cast<int*>(ws + al(4 * n) + 2 * al(n));
+    const long long nblocks = (n + RANK_CHUNK - 1) / RANK_CHUNK;
+    int rc = run_ccl(mask, 1, d, connectivity_full != 0, false, parent, st);
+    if (rc) return rc;
+    root_count_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(d, parent, block_counts);
+    block_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, n_labels);
+    root_assign_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(d, parent, block_counts, labels);
+    label_propagate_kernel<<<gs(n), THREADS, 0, st>>>(d, parent, labels);
+    return nb::check_launch("ccl_label");
+}
+
+}  // extern "C"

@@ -179,6 +179,7 @@ class FrangiEngine3D:
         self.fd = params.fd_spacing_f32()
         self._fd_c = self.fd.ctypes.data_as(C.POINTER(C.c_float))
         self.launches = 0
+        self.profile = None   # set to a list to record (name, start, end) CUDA events per C-ABI call
         # hooks for the multi-GPU driver (identity on one GPU)
         self.exchange_halo = lambda buf, depth: None
         self.reduce_hist_minmax = lambda state: None
@@ -195,7 +196,23 @@ class FrangiEngine3D:
 
     def _call(self, name, *args):
         self.launches += 1
+        if self.profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _cabi.check(getattr(self.lib, name)(*args), name)
+            e1.record()
+            self.profile.append((name, e0, e1))
+            return
         _cabi.check(getattr(self.lib, name)(*args), name)
+
+    def profile_summary(self):
+        """{call name: (launches, total ms)} from the CUDA events recorded while ``self.profile`` was a list."""
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for name, e0, e1 in self.profile or []:
+            n, ms = out.get(name, (0, 0.0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1))
+        return out
 
     # -- thresholds from a sample buffer --------------------------------------------------------
     def _histogram(self, samples, n, transform, divisor_ptr):

@@ -1,0 +1,155 @@
+"""CPU-only checks: host scalar logic vs the oracle, C ABI surface, device math compiled for the host."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_sigma_schedule_and_strides_match_oracle():
+    from nellie_b200.engine import FilterParams, sample_strides
+    from oracle import pipeline as P
+    for dim_res, no_z in [({"X": 0.0655, "Y": 0.0655, "Z": 0.25, "T": 4.5}, False),
+                          ({"X": 0.1, "Y": 0.1, "Z": 0.1, "T": 1}, False),
+                          ({"X": 0.125, "Y": 0.125, "Z": 0.125, "T": 1}, False),
+                          ({"X": 0.1, "Y": 0.1, "Z": None, "T": 1}, True),
+                          ({"X": 0.5, "Y": 0.5, "Z": 1.0, "T": 1}, False)]:
+        for kw in [{}, dict(min_radius_um=0.25, max_radius_um=0.675), dict(min_radius_um=1.0, max_radius_um=1.0)]:
+            p = FilterParams(dim_res=dim_res, no_z=no_z, **kw)
+            s = P.FrameSpec(dim_res=dim_res, no_z=no_z, **kw)
+            assert p.sigma_list() == P.sigma_schedule(s)
+            prev = 0.0
+            for sg in p.sigma_list():
+                assert p.delta_sigma_vec(prev, sg) == P.delta_sigma_vector(s, prev, sg)
+                prev = sg
+    for shape in [(17, 192, 279), (512, 512, 512), (1024, 1024, 1024), (2048, 2048), (40, 128, 200), (3, 5)]:
+        assert sample_strides(shape, 10 ** 6) == P.sample_strides(shape, 10 ** 6)
+    # BASELINE config #2 derivation: exactly 4 sigmas 1.0..1.6
+    p = FilterParams(dim_res={"X": 0.125, "Y": 0.125, "Z": 0.125}, min_radius_um=0.25, max_radius_um=0.675)
+    assert np.allclose(p.sigma_list(), [1.0, 1.2, 1.4, 1.6])
+
+
+def test_gaussian_taps_match_scipy_kernel():
+    from scipy.ndimage import _filters
+    from nellie_b200.engine import gaussian_taps
+    for sd in [0.441, 0.5, 1.25, 1.908, 2.294, 3.0]:
+        w, r = gaussian_taps(sd, 3.0)
+        ref = _filters._gaussian_kernel1d(sd, 0, int(3.0 * sd + 0.5))
+        assert r == (len(ref) - 1) // 2
+        assert np.array_equal(w, ref[r:]) and np.array_equal(w, ref[:r + 1][::-1])
+
+
+def test_cabi_exports_every_declared_symbol():
+    """The shared library loads and exports every function include/nellie_b200.h declares."""
+    from nellie_b200 import _cabi, build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "nellie_b200.h")).read()
+    declared = set(re.findall(r"\b(nb200_[a-z0-9_]+)\s*\(", header))
+    declared -= {"nb200_vol"}
+    lib = C.CDLL(_cabi.lib_path())
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert declared == set(_cabi._SIGS), declared ^ set(_cabi._SIGS)
+    assert _cabi.load().nb200_abi_version() == 1
+
+
+def test_product_has_no_cpu_fallback_and_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "nellie_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert not re.search(r"^\s*(import|from)\s+(scipy|cupy)", src, re.M), f
+
+
+@pytest.fixture(scope="module")
+def hostmath():
+    so = os.path.join(ROOT, "oracle", "_build", "devmath_host.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-mfma", "-shared", "-fPIC", "-o", so,
+                    os.path.join(ROOT, "oracle", "devmath_host.cpp")], check=True)
+    return C.CDLL(so)
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_np_expf_is_bit_exact(hostmath):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([-rng.random(400_000) * 30, -rng.random(200_000) * 1e-3,
+                        -np.exp(rng.uniform(-40, 5, 400_000)), [-0.0, 0.0, -np.inf, -104.0, -88.0, -87.5, np.nan]]
+                       ).astype(np.float32)
+    y = np.empty_like(x)
+    hostmath.hm_expf(_vp(x), _vp(y), C.c_long(x.size))
+    with np.errstate(all="ignore"):
+        ref = np.exp(x)
+    assert np.array_equal(y.view(np.uint32)[~np.isnan(ref)], ref.view(np.uint32)[~np.isnan(ref)])
+    assert np.isnan(y[np.isnan(ref)]).all()
+
+
+def _eig_ref(h6):
+    H = np.empty((len(h6), 3, 3), np.float32)
+    H[:, 0, 0], H[:, 0, 1], H[:, 0, 2], H[:, 1, 1], H[:, 1, 2], H[:, 2, 2] = h6.T
+    H[:, 1, 0], H[:, 2, 0], H[:, 2, 1] = H[:, 0, 1], H[:, 0, 2], H[:, 1, 2]
+    ev = np.linalg.eigvalsh(H)
+    return np.take_along_axis(ev, np.argsort(np.abs(ev), axis=1), axis=1)
+
+
+def test_eig3_matches_eigvalsh_rounded_to_f32(hostmath):
+    rng = np.random.default_rng(1)
+    n = 300_000
+    cases = [rng.standard_normal((n, 6)).astype(np.float32) * 1000]
+    t = rng.standard_normal((n, 6)).astype(np.float32)
+    t[:, [1, 2, 4]] *= 1e-3
+    cases.append(t)
+    t = rng.standard_normal((n, 6)).astype(np.float32) * 1e-2
+    t[:, [0, 3, 5]] += 5
+    cases.append(t)
+    z = np.zeros((64, 6), np.float32)
+    z[::2, [0, 3, 5]] = 3
+    cases.append(z)
+    for h6 in cases:
+        h6 = np.ascontiguousarray(h6)
+        out = np.empty((len(h6), 3), np.float32)
+        hostmath.hm_eig3(_vp(h6), _vp(out), C.c_long(len(h6)), C.c_int(2))
+        assert np.array_equal(out, _eig_ref(h6))
+    # near-degenerate tubes (lambda2 ~ lambda3): the cubic is ill-conditioned there; stay within 1 ulp
+    v = rng.standard_normal((n, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    lam = rng.uniform(-1000, -10, (n, 1, 1))
+    M = lam * (np.eye(3)[None] - v[:, :, None] * v[:, None, :]) + rng.standard_normal((n, 3, 3)) * 0.01
+    M = (M + M.transpose(0, 2, 1)) / 2
+    h6 = np.ascontiguousarray(np.stack([M[:, 0, 0], M[:, 0, 1], M[:, 0, 2], M[:, 1, 1], M[:, 1, 2], M[:, 2, 2]], 1),
+                              dtype=np.float32)
+    out = np.empty((n, 3), np.float32)
+    hostmath.hm_eig3(_vp(h6), _vp(out), C.c_long(n), C.c_int(2))
+    ref = _eig_ref(h6)
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(out.astype(np.float64) - ref) <= 1.2e-7 * scale).all()
+    assert (out != ref).any(axis=1).mean() < 2e-3
+
+
+def test_vesselness_matches_oracle_bitwise(hostmath):
+    from oracle import pipeline as P
+    rng = np.random.default_rng(2)
+    ev = (rng.standard_normal((500_000, 3)) * 50).astype(np.float32)
+    ev = np.take_along_axis(ev, np.argsort(np.abs(ev), axis=1), axis=1)
+    ev[:10] = 0
+    spec = P.FrameSpec(dim_res={"X": 1, "Y": 1, "Z": 1})
+    for gamma_sq in [2.0 * 104.2 ** 2, 3.7, 1e-9]:
+        ref = P.vesselness(ev.copy(), spec, gamma_sq)
+        out = np.empty(len(ev), np.float32)
+        hostmath.hm_vesselness3(_vp(np.ascontiguousarray(ev)), _vp(out), C.c_long(len(ev)), C.c_float(0.5),
+                                C.c_float(0.5), C.c_float(gamma_sq))
+        assert np.array_equal(out, ref)
+    spec2 = P.FrameSpec(dim_res={"X": 1, "Y": 1}, no_z=True)
+    ev2 = np.ascontiguousarray(ev[:, 1:])
+    ref = P.vesselness(ev2.copy(), spec2, 77.0)
+    out = np.empty(len(ev2), np.float32)
+    hostmath.hm_vesselness2(_vp(ev2), _vp(out), C.c_long(len(ev2)), C.c_float(0.5), C.c_float(77.0))
+    assert np.array_equal(out, ref)
