@@ -1,0 +1,265 @@
+"""Benchmark of the Filter hot path (Frangi + eigen) — BASELINE.json metric: voxels/s on a 1024^3 fp32
+synthetic volume, 6 sigmas, at 1/2/4/8 B200 (Z-sharded with halo exchange), plus achieved HBM GB/s
+of the fused Hessian+eigen kernel (K3) against the measured copy peak.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3            # our arm (one JSON line on stdout)
+    python bench.py --impl reference --steps 1 --warmup 0    # CPU arm: the oracle port on host cores
+
+A "step" is one pass of the whole per-frame path (filtering.py:1007-1031: cascaded blur, per-sigma
+thresholds, fused Hessian/eig/vesselness, percentile + opening) over the resident volume.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "voxels/s Frangi+eig (Filter) on 1024^3 fp32, 6 sigmas"
+SIGMAS_CFG3 = [1.0, 1.4, 1.8, 2.2, 2.6, 3.0]
+DIM_RES_CFG3 = {"X": 0.1, "Y": 0.1, "Z": 0.1, "T": 1.0}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (numpy/scipy restatement of the reference) on host cores
+# --------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    size, seed = args
+    from nellie_b200.phantoms import tubular_phantom_np
+    from oracle import pipeline as P
+    raw = tubular_phantom_np((size,) * 3, seed=seed)
+    spec = P.FrameSpec(dim_res=DIM_RES_CFG3, no_z=False, sigmas=SIGMAS_CFG3)
+    t0 = time.perf_counter()
+    out = P.filter_frame(raw, spec)
+    return time.perf_counter() - t0, int(raw.size), float(out.max())
+
+
+def cpu_baseline(size=112, procs=1):
+    """Time the oracle on `procs` independent size^3 crops of the workload (one process per crop: the
+    reference path is single-threaded, frames/crops are its only parallel axis)."""
+    if procs == 1:
+        res = [_cpu_worker((size, 1000))]
+        wall = res[0][0]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(procs) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(size, 1000 + i) for i in range(procs)])
+            wall = time.perf_counter() - t0
+    vox = sum(r[1] for r in res)
+    return {"value": vox / wall, "unit": "voxels/s", "cores": procs, "kind": "port",
+            "sample": f"{procs} x {size}^3 crop(s) of the tubular phantom, 6 sigmas, oracle.pipeline.filter_frame, "
+                      f"{wall:.1f} s wall"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    procs = max(1, (os.cpu_count() or 1))
+    steps = max(1, args.steps)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_baseline(args.cpu_size, procs)
+    t_all0 = time.perf_counter()
+    for _ in range(steps):
+        vals.append(cpu_baseline(args.cpu_size, procs))
+    wall = time.perf_counter() - t_all0
+    v = float(np.mean([x["value"] for x in vals]))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "voxels/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 accumulate / eigvalsh)", "data": "synthetic",
+            "config": {"workload": f"reference CPU path (oracle port) on {procs} x {args.cpu_size}^3 crops of the "
+                                   "1024^3 tubular phantom workload, 6 sigmas", "sigmas": SIGMAS_CFG3},
+            "cpu_baseline": dict(vals[-1], value=v),
+            "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from nellie_b200.engine import FilterParams, FrangiEngine3D
+    from nellie_b200.phantoms import tubular_phantom
+
+    n = args.size
+    shape = (n, n, n)
+    params = FilterParams(dim_res=DIM_RES_CFG3, no_z=False, sigmas=SIGMAS_CFG3)
+    if world > 1:
+        from nellie_b200.sharding import ZShardedFilter
+        runner = ZShardedFilter(shape, params, dev)
+        frame = runner.make_phantom_slab(seed=3)
+        eng = runner.engine
+        step = lambda: runner.filter_frame(frame)                     # noqa: E731
+    else:
+        eng = FrangiEngine3D(shape, params, device=dev)
+        frame = tubular_phantom(shape, seed=3, device=dev, n_tubes=args.tubes)
+        step = lambda: eng.filter_frame(frame)                        # noqa: E731
+        runner = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.launches = 0
+    eng.profile = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = eng.profile_summary()
+    eng.profile = None
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    voxels = float(n) ** 3
+    value = voxels * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    if world == 1:
+        host_in = torch.empty(shape, dtype=torch.float32).pin_memory()
+        host_in.copy_(frame)
+        host_out = torch.empty(shape, dtype=torch.float32).pin_memory()
+        staging = torch.empty(shape, dtype=torch.float32, device=dev)
+
+        def e2e_step():
+            staging.copy_(host_in, non_blocking=True)
+            out = eng.filter_frame(staging)
+            host_out.copy_(out, non_blocking=True)
+
+        e2e_step()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        e2e = {"value": voxels * args.steps / dt, "unit": "voxels/s", "h2d_bytes_per_step": int(voxels * 4),
+               "d2h_bytes_per_step": int(voxels * 4)}
+    elif runner is not None:
+        e2e = runner.e2e(args.steps, frame)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, which = measured_peaks()
+    k3_n, k3_ms = prof.get("nb200_frangi_accumulate", (0, 0.0))
+    vox_per_launch = voxels / world
+    roofline = None
+    if k3_n:
+        achieved = 12.0 * vox_per_launch / (k3_ms / k3_n * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "frangi_accumulate_kernel (K3: Hessian+eig+vesselness+max/AND)",
+                    "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": which, "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                    "algorithmic_bytes_per_launch": 12.0 * vox_per_launch, "avg_launch_ms": k3_ms / k3_n,
+                    "share_of_step": k3_ms / ms}
+    breakdown = {k: {"launches": v[0], "ms_per_step": v[1] / args.steps} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    cpu = cpu_baseline(args.cpu_size, 1) if (world == 1 and not args.no_cpu) else None
+    line = {"metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (f64 blur accumulate, f64-polished eigenvalues)", "data": "synthetic",
+            "config": {"workload": f"synthetic {n}^3 fp32 tubular phantom, {len(SIGMAS_CFG3)} sigmas "
+                                   f"{SIGMAS_CFG3}, dim_res 0.1 um isotropic" + (f", Z-sharded over {world} GPUs with halo exchange" if world > 1 else ""),
+                       "l2_policy": "inputs larger than L2 (4 B x voxels per buffer >> 126 MB)", "seed": 3},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": eng.launches, "roofline": roofline, "cpu_baseline": cpu,
+            "kernel_ms_per_step": breakdown}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=1024, help="edge of the cubic volume (1024 = BASELINE config #3)")
+    ap.add_argument("--tubes", type=int, default=None)
+    ap.add_argument("--cpu-size", type=int, default=112, help="edge of the crop the CPU baseline runs")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -156,6 +156,15 @@ int nb200_percentile(const float* samples, long long n, double q_percent, long l
 int nb200_finalize_opening(const float* acc, float* out, const nb200_vol* vol, const double* thr, void* stream);
 int nb200_finalize_opening_2d(const float* v, float* out, int ny, int nx, const double* thr, void* stream);
 
+/* ---- F10: 2-D multi-scale LoG blobness (filtering.py:772-795, :927-930) ------------------------
+ * t0/t1: the two separable second-derivative Gaussians of scipy.ndimage.gaussian_laplace (built with
+ * nb200_gauss_axis and order-2 taps); acc: the sigma-loop accumulator (>= 0 alive, -1 dead).
+ * accumulate: L = first ? cur : max(L, cur), cur = (-(t0+t1)) * sigma_sq * alive.
+ * combine: V = max(max(acc,0), max((max(L,0) / (max L + 1e-12)) / 10, 0)); max_bits: device int64 scratch. */
+int nb200_log2d_accumulate(const float* t0, const float* t1, const float* acc, float sigma_sq, int first,
+                           long long n, float* L, void* stream);
+int nb200_log2d_combine(const float* acc, const float* L, long long n, long long* max_bits, float* v, void* stream);
+
 /* ---- L4/L5: Label._get_labels (labelling.py:467-509, :546-556) -------------------------------
  * threshold (strict >, optional intensity gate on `raw`) -> fill holes (3-D only) -> 26-/8-connected
  * components -> drop components smaller than min_area -> 3^d majority smoothing -> components again.

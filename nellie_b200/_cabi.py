@@ -62,6 +62,8 @@ _SIGS = {
     "nb200_percentile": ([_p, _ll, C.c_double, _p, _p, _p], C.c_int),
     "nb200_finalize_opening": ([_p, _p, C.POINTER(Vol), _p, _p], C.c_int),
     "nb200_finalize_opening_2d": ([_p, _p, C.c_int, C.c_int, _p, _p], C.c_int),
+    "nb200_log2d_accumulate": ([_p, _p, _p, C.c_float, C.c_int, _ll, _p, _p], C.c_int),
+    "nb200_log2d_combine": ([_p, _p, _ll, _p, _p, _p], C.c_int),
     "nb200_label_workspace_bytes": ([C.c_int, C.c_int, C.c_int], C.c_size_t),
     "nb200_label_frame": ([_p, _p, C.c_int, C.c_float, _p, C.c_int, C.c_int, C.c_int, _ll, C.c_int, _p, _p, _p, _p],
                           C.c_int),

@@ -33,6 +33,7 @@ __device__ __forceinline__ int ld_parent(const int* parent, long long i) {
 }
 
 __device__ __forceinline__ int find_root(int* parent, int x) {
+    if (x < 0) return x;   // OUTSIDE handed back by a lost atomicMin race
     int p = ld_parent(parent, x);
     while (p != x && p >= 0) {
         const int gp = ld_parent(parent, p);
@@ -41,6 +42,18 @@ __device__ __forceinline__ int find_root(int* parent, int x) {
         p = gp;
     }
     return p;  // own index for a root, OUTSIDE for a border-connected background tree
+}
+
+// read-only walk (no path halving): used by the flatten pass, where a stale halving store from
+// another thread could overwrite a voxel's final root with an intermediate ancestor
+__device__ __forceinline__ int find_root_ro(const int* parent, int x) {
+    if (x < 0) return x;
+    int p = ld_parent(parent, x);
+    while (p != x && p >= 0) {
+        x = p;
+        p = ld_parent(parent, x);
+    }
+    return p;
 }
 
 __device__ __forceinline__ void unite(int* parent, int a, int b) {
@@ -162,7 +175,7 @@ ccl_flatten_kernel(Dims d, int* __restrict__ parent) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
          i += (long long)gridDim.x * blockDim.x) {
         if (parent[i] == NOT_IN_SET) continue;
-        const int r = find_root(parent, (int)i);
+        const int r = find_root_ro(parent, (int)i);
         parent[i] = r;
     }
 }

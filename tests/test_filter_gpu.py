@@ -68,3 +68,20 @@ def test_filter_matches_oracle_on_fresh_phantom():
     got = f.filter_frame_host(raw)
     assert np.array_equal(got > 0, ref > 0)
     assert frangi_tolerance(got, ref).all()
+
+
+def test_filter_2d_matches_reference():
+    """2-D path: closed-form 2x2 eigenvalues + LoG blobness on the blurred frame (filtering.py:676-690, :772-795)."""
+    g = load_golden("phantom2d")
+    f = _filter_for(g)
+    pre = f._run_frame(0)
+    rec = f._engine.sigma_records()
+    assert rec[:, 0].tolist() == g["gamma"].tolist()
+    assert rec[:, 2].tolist() == g["frob_thr"].tolist()
+    ok = frangi_tolerance(pre, g["frangi_pre"])
+    assert ok.all(), f"{(~ok).sum()} pixels outside tolerance"
+    assert np.array_equal(pre > 0, g["frangi_pre"] > 0)
+    print("phantom2d: pre-mask bit mismatches =", int((pre != g["frangi_pre"]).sum()))
+    fin = f.filter_frame_host(g["raw"])
+    assert np.array_equal(fin > 0, g["frangi"] > 0)
+    assert frangi_tolerance(fin, g["frangi"]).all()

@@ -43,6 +43,16 @@ def test_gaussian_taps_match_scipy_kernel():
         assert np.array_equal(w, ref[r:]) and np.array_equal(w, ref[:r + 1][::-1])
 
 
+def test_order2_taps_match_scipy_kernel():
+    from scipy.ndimage import _filters
+    from nellie_b200.engine2d import gaussian_taps_order2
+    for sd in [1.25, 1.667, 2.083, 2.5, 2.917]:
+        w, r = gaussian_taps_order2(sd, 4.0)
+        ref = _filters._gaussian_kernel1d(sd, 2, int(4.0 * sd + 0.5))[::-1]
+        assert r == (len(ref) - 1) // 2
+        assert np.array_equal(w, ref[r:]) and np.array_equal(w, ref[:r + 1][::-1])
+
+
 def test_cabi_exports_every_declared_symbol():
     """The shared library loads and exports every function include/nellie_b200.h declares."""
     from nellie_b200 import _cabi, build

@@ -124,6 +124,11 @@ def test_label_frame_matches_oracle_random_blobs(seed):
     field = ndi.gaussian_filter(rng.standard_normal((48, 80, 96)), 2.0 + seed).astype(np.float32)
     field = (field - field.min()) / (field.max() - field.min())
     field[rng.random(field.shape) < 0.003] = 1.0
+    field[10:22, 20:40, 30:60] = 0.9            # a solid block ...
+    field[14:18, 26:34, 38:52] = 0.1            # ... with an enclosed cavity (filled by binary_fill_holes)
+    field[15, 29, 36:40] = 0.1                  # and one that tunnels... stays inside, still enclosed
+    field[30:34, 50:60, 10:30] = 0.9
+    field[31:33, 53:57, 0:20] = 0.1             # a cavity open to the frame border: must NOT be filled
     dim_res = {"X": 0.2, "Y": 0.2, "Z": 0.25, "T": 1.0}
     spec = P.FrameSpec(dim_res=dim_res, no_z=False)
     stages = {}
