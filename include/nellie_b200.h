@@ -70,6 +70,8 @@ typedef struct nb200_vol {
 #define NB200_SP_STATUS 6     /* 0 ok, 1 degenerate histogram (reference would raise) */
 #define NB200_SP_TRI 7
 #define NB200_SP_OTSU 8
+#define NB200_SP_UNSAFE 9     /* 1.0 when the blurred volume holds values outside the exponent range the fast
+                                 constant-divisor division was verified on: kernels fall back to IEEE division */
 #define NB200_SP_WORDS 12
 
 /* int64[NB200_HS_WORDS] device record reduced by nb200_hessian_stats */
@@ -129,16 +131,31 @@ int nb200_finalize_label_threshold(const long long* state, int log_domain, doubl
  * every voxel of [zc0,zc1): reduces max|component| and max frob_sq into hstats and writes
  * sqrt(frob_sq) at the lattice points into `frob_samples` (layout of nb200_lattice_sample).
  * spacing[6] (HOST, float): {fl32(hz), fl32(2hz), fl32(hy), fl32(2hy), fl32(hx), fl32(2hx)}. */
-int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* spacing,
-                        int sz, int sy, int sx, float* frob_samples, long long* hstats, void* stream);
+int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
+                        const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
+                        void* stream);
+/* Division mode for one grid-spacing divisor d = fl32(h) or fl32(2h) (synchronous, init time only):
+ *   2 (NB200_DIV_POW2)  d is a power of two: multiply by the exact reciprocal;
+ *   1 (NB200_DIV_FAST)  q = fma(fma(-n*r, d, n), r, n*r), r = RN(1/d), verified HERE bit-for-bit against IEEE
+ *                       division for every numerator with exponent in [-90, 90] and +-0;
+ *   0 (NB200_DIV_IEEE)  plain correctly rounded division.
+ * A launch uses one mode for all six divisors: the weakest of their modes. */
+#define NB200_DIV_IEEE 0
+#define NB200_DIV_FAST 1
+#define NB200_DIV_POW2 2
+int nb200_divisor_mode(float d, int* mode_out, void* stream);
 int nb200_hstats_reset(long long* hstats, void* stream);
+/* The six second derivatives themselves (tests / diagnostics): out6 = 6 volumes of the buffer shape in the
+ * order d0d0, d1d0, d2d0, d1d1, d2d1, d2d2 (the reference's hxx, hxy, hxz, hyy, hyz, hzz; axes 0,1,2 = Z,Y,X). */
+int nb200_hessian_components(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
+                             float* out6, void* stream);
 
 /* ---- F4-F9 fused: Hessian + Frobenius mask + eigenvalues + vesselness + max/AND ------------
  * (filtering.py:842-851).  acc holds max-over-sigma vesselness for live voxels and -1 for
  * voxels that failed the mask at any non-skipped sigma; acc must be zero-filled before the
  * first sigma.  Reads gamma_sq / frob cut / max_abs / skip from the device record `sp`. */
 int nb200_frangi_accumulate(const float* gauss, float* acc, const nb200_vol* vol, const float* spacing,
-                            float alpha_sq, float beta_sq, const double* sp, void* stream);
+                            int div_mode, float alpha_sq, float beta_sq, const double* sp, void* stream);
 /* 2-D variant (closed-form 2x2 eigenvalues, filtering.py:676-690, :737-741); spacing[4] = y,x */
 int nb200_frangi_accumulate_2d(const float* gauss, float* acc, int ny, int nx, const float* spacing,
                                float beta_sq, const double* sp, void* stream);

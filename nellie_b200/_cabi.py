@@ -13,7 +13,8 @@ from . import build as _build
 HIST_WORDS = 3 + 256
 SP_WORDS = 12
 HS_WORDS = 2
-SP_GAMMA, SP_GAMMA_SQ, SP_FROB_THR, SP_FROB_CUT, SP_MAX_ABS, SP_SKIP, SP_STATUS, SP_TRI, SP_OTSU = range(9)
+SP_GAMMA, SP_GAMMA_SQ, SP_FROB_THR, SP_FROB_CUT, SP_MAX_ABS, SP_SKIP, SP_STATUS, SP_TRI, SP_OTSU, SP_UNSAFE = range(10)
+DIV_IEEE, DIV_FAST, DIV_POW2 = 0, 1, 2
 TF_NONE, TF_DIV, TF_LOG10 = 0, 1, 2
 SELECT_WORDS = 2048 + 8
 
@@ -54,9 +55,13 @@ _SIGS = {
     "nb200_finalize_frob": ([_p, _p, C.c_double, C.c_double, _p, _p], C.c_int),
     "nb200_finalize_max_abs": ([_p, _p, _p], C.c_int),
     "nb200_finalize_label_threshold": ([_p, C.c_int, _p, _p], C.c_int),
-    "nb200_hessian_stats": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, _p, _p, _p], C.c_int),
+    "nb200_hessian_stats": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p],
+                            C.c_int),
+    "nb200_hessian_components": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, _p], C.c_int),
+    "nb200_divisor_mode": ([C.c_float, C.POINTER(C.c_int), _p], C.c_int),
     "nb200_hstats_reset": ([_p, _p], C.c_int),
-    "nb200_frangi_accumulate": ([_p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_float, C.c_float, _p, _p], C.c_int),
+    "nb200_frangi_accumulate": ([_p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, _p, _p],
+                                C.c_int),
     "nb200_frangi_accumulate_2d": ([_p, _p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_float, _p, _p], C.c_int),
     "nb200_hessian_stats_2d": ([_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int, _p, _p, _p], C.c_int),
     "nb200_percentile": ([_p, _ll, C.c_double, _p, _p, _p], C.c_int),

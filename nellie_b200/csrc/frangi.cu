@@ -9,153 +9,264 @@
 // so the reference's separate bool `masks` volume never exists.  Algorithmic HBM traffic per
 // sigma: K2 reads g (4 B/voxel); K3 reads g, reads+writes acc (12 B/voxel).
 //
-// Tiling (both kernels): a CTA owns a (TZ x TY x TX) brick of outputs and stages the brick plus
-// a 2-voxel halo of g in shared memory with coalesced 128-byte row loads; the 19-point stencil
-// and all re-use then run out of shared memory, so g is read from HBM ~once (halo overhead only).
+// Both kernels are epilogues of the Z-marching Hessian in hessian_march.cuh (shared-memory ring of
+// blurred planes fed by cp.async, first-derivative planes shared between the second derivatives,
+// 4 voxels per thread with 128-bit shared/global accesses).
 #include "common.cuh"
 #include "hessian.cuh"
+#include "hessian_march.cuh"
 
 namespace {
 
-constexpr int TX = 64, TY = 8, TZ = 8;      // outputs per CTA
-constexpr int HALO = 2;
-constexpr int SX = TX + 2 * HALO;           // 68
-constexpr int SY = TY + 2 * HALO;           // 12
-constexpr int SZ = TZ + 2 * HALO;           // 12
-constexpr int SXP = SX + 1;                 // padded row pitch (floats)
-constexpr int NTHREADS = 256;
-
-struct Tile {
-    float g[SZ][SY][SXP];
-};
-
-// stage brick + halo; coordinates outside the GLOBAL frame are clamped (their values are never
-// used: the one-sided rules at the frame border only touch in-frame samples)
-__device__ __forceinline__ void load_tile(Tile& t, const float* __restrict__ g, const nb200_vol& v,
-                                          int zb0, int y0, int x0) {
-    const long long plane = (long long)v.ny * v.nx;
-    const int zlo = max(-v.zg_off, 0), zhi = min(v.nz_glob - v.zg_off, v.nz_buf) - 1;  // valid buffer planes
-    for (int i = threadIdx.x; i < SZ * SY * SX; i += NTHREADS) {
-        const int lx = i % SX;
-        const int ly = (i / SX) % SY;
-        const int lz = i / (SX * SY);
-        int zb = zb0 - HALO + lz, y = y0 - HALO + ly, x = x0 - HALO + lx;
-        zb = min(max(zb, zlo), zhi);
-        y = min(max(y, 0), v.ny - 1);
-        x = min(max(x, 0), v.nx - 1);
-        t.g[lz][ly][lx] = __ldg(g + (long long)zb * plane + (long long)y * v.nx + x);
-    }
-}
-
-struct TileLoad {
-    const Tile* t;
-    int lz, ly, lx;
-    __device__ __forceinline__ float operator()(int dz, int dy, int dx) const {
-        return t->g[lz + dz][ly + dy][lx + dx];
-    }
-};
-
-__device__ __forceinline__ void brick_origin(const nb200_vol& v, int& zb0, int& y0, int& x0, bool& valid) {
-    const int nbx = (v.nx + TX - 1) / TX, nby = (v.ny + TY - 1) / TY;
-    long long b = blockIdx.x;
-    const int bx = (int)(b % nbx); b /= nbx;
-    const int by = (int)(b % nby); b /= nby;
-    zb0 = v.zc0 + (int)b * TZ;
-    y0 = by * TY;
-    x0 = bx * TX;
-    valid = zb0 < v.zc1;
-}
+using hm::Hess4;
 
 // --------------------------------------------------------------------------------------------
-// K2: max |component|, max frob_sq, sqrt(frob_sq) at the sampling lattice
+// epilogues
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS)
-hessian_stats_kernel(const float* __restrict__ g, nb200_vol v, nb::Spacing3 sp, int sz, int sy, int sx,
-                     int g_first, int ly_n, int lx_n, float* __restrict__ frob_samples,
-                     long long* __restrict__ hstats) {
-    __shared__ Tile tile;
-    __shared__ float red_a[NTHREADS / 32], red_f[NTHREADS / 32];
-    int zb0, y0, x0; bool valid;
-    brick_origin(v, zb0, y0, x0, valid);
-    load_tile(tile, g, v, zb0, y0, x0);
-    __syncthreads();
-    const int n[3] = {v.nz_glob, v.ny, v.nx};
+struct StatsParams {
+    int sz, sy, sx, g_first, ly_n, lx_n;
+    float* frob_samples;
+    long long* hstats;
+};
+
+// frob_sq of 4 voxels, evaluated exactly like filtering.py:538-543 (each product and each sum rounded once).
+// Squares run packed (FMUL2); the sums are scalar FADDs on purpose: ptxas contracts a packed multiply that
+// feeds a packed add into FFMA2 even for mul.rn/add.rn.f32x2 and --fmad=false, which would skip a rounding.
+__device__ __forceinline__ float4 frob_sq4(const Hess4& h) {
+    auto half = [](float2 zz, float2 zy, float2 zx, float2 yy, float2 yx, float2 xx) -> float2 {
+        const float2 a = __fmul2_rn(zz, zz), b = __fmul2_rn(yy, yy), c = __fmul2_rn(xx, xx);
+        const float2 d = __fmul2_rn(zy, zy), e = __fmul2_rn(zx, zx), f = __fmul2_rn(yx, yx);
+        float2 r;
+        r.x = ((a.x + b.x) + c.x) + 2.0f * ((d.x + e.x) + f.x);
+        r.y = ((a.y + b.y) + c.y) + 2.0f * ((d.y + e.y) + f.y);
+        return r;
+    };
+    const float2 lo = half(make_float2(h.zz.x, h.zz.y), make_float2(h.zy.x, h.zy.y), make_float2(h.zx.x, h.zx.y),
+                           make_float2(h.yy.x, h.yy.y), make_float2(h.yx.x, h.yx.y), make_float2(h.xx.x, h.xx.y));
+    const float2 hi = half(make_float2(h.zz.z, h.zz.w), make_float2(h.zy.z, h.zy.w), make_float2(h.zx.z, h.zx.w),
+                           make_float2(h.yy.z, h.yy.w), make_float2(h.yx.z, h.yx.w), make_float2(h.xx.z, h.xx.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+__device__ __forceinline__ float absmax4(const float4& a) {
+    return fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w)));
+}
+
+struct StatsEpi {
+    const StatsParams& p;
+    const nb200_vol& v;
     float m_abs = 0.0f, m_frob = 0.0f;
-    const int tx = threadIdx.x % TX, ty0 = threadIdx.x / TX;   // 64 x 4 threads
-    for (int lz = 0; lz < TZ; ++lz) {
-        const int zb = zb0 + lz;
-        if (zb >= v.zc1) break;
-        const int zg = zb + v.zg_off;
-        for (int ly = ty0; ly < TY; ly += NTHREADS / TX) {
-            const int y = y0 + ly, x = x0 + tx;
-            if (y >= v.ny || x >= v.nx) continue;
-            TileLoad L{&tile, lz + HALO, ly + HALO, tx + HALO};
-            float a, b, c, d, e, f;
-            nb::hessian3(L, zg, y, x, n, sp, a, b, c, d, e, f);
-            const float fs = nb::frob_sq3(a, b, c, d, e, f);
-            m_abs = fmaxf(m_abs, fmaxf(fmaxf(fmaxf(fabsf(a), fabsf(b)), fmaxf(fabsf(c), fabsf(d))),
-                                       fmaxf(fabsf(e), fabsf(f))));
-            m_frob = fmaxf(m_frob, fs);
-            if (frob_samples && (zg % sz == 0) && (y % sy == 0) && (x % sx == 0)) {
-                const long long k = ((long long)((zg - g_first) / sz) * ly_n + y / sy) * lx_n + x / sx;
-                frob_samples[k] = sqrtf(fs);
+    int xmask = 0, xlat = 0;            // lattice columns inside this thread's 4-voxel group (loop invariant)
+    int ylat[hm::TY / hm::NW];          // lattice row index of each output row, or -1
+    long long zrow = -1;                // lattice plane offset of the current plane, or -1 (uniform)
+    __device__ StatsEpi(const StatsParams& p_, const nb200_vol& v_, int x0, int y0) : p(p_), v(v_) {
+        const int x = x0 + 4 * (threadIdx.x & 31);
+        for (int k = 0; k < 4; ++k) xmask |= ((x + k) % p.sx == 0) ? (1 << k) : 0;
+        xlat = (x + p.sx - 1) / p.sx;
+        for (int i = 0; i < hm::TY / hm::NW; ++i) {
+            const int y = y0 + (threadIdx.x >> 5) + i * hm::NW;
+            ylat[i] = (p.frob_samples && xmask && (y % p.sy == 0)) ? y / p.sy : -1;
+        }
+    }
+    __device__ __forceinline__ void plane(int zg) {
+        zrow = (zg % p.sz == 0) ? (long long)((zg - p.g_first) / p.sz) * p.ly_n : -1;
+    }
+    __device__ __forceinline__ bool skip4(int, int, int, int, int) { return false; }
+    __device__ __forceinline__ void voxels4(int row, int, int, int x, int nvalid, const Hess4& h) {
+        const float4 fs = frob_sq4(h);
+        if (nvalid == 4) {
+            m_abs = fmaxf(m_abs, fmaxf(fmaxf(fmaxf(absmax4(h.zz), absmax4(h.zy)), fmaxf(absmax4(h.zx), absmax4(h.yy))),
+                                       fmaxf(absmax4(h.yx), absmax4(h.xx))));
+            m_frob = fmaxf(m_frob, fmaxf(fmaxf(fs.x, fs.y), fmaxf(fs.z, fs.w)));
+        } else {
+            const float* c[6] = {&h.zz.x, &h.zy.x, &h.zx.x, &h.yy.x, &h.yx.x, &h.xx.x};
+            const float* f = &fs.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < nvalid) {
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) m_abs = fmaxf(m_abs, fabsf(c[j][k]));
+                    m_frob = fmaxf(m_frob, f[k]);
+                }
+        }
+        if (zrow >= 0 && ylat[row] >= 0) {            // lattice row: a few threads per plane
+            const float* f = &fs.x;
+            long long idx = (zrow + ylat[row]) * p.lx_n + xlat;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < nvalid && (xmask >> k & 1)) p.frob_samples[idx++] = sqrtf(f[k]);
+        }
+    }
+    __device__ void finish() {
+        __shared__ float red_a[hm::NW], red_f[hm::NW];
+        for (int o = 16; o > 0; o >>= 1) {
+            m_abs = fmaxf(m_abs, __shfl_xor_sync(0xffffffffu, m_abs, o));
+            m_frob = fmaxf(m_frob, __shfl_xor_sync(0xffffffffu, m_frob, o));
+        }
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) { red_a[w] = m_abs; red_f[w] = m_frob; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < hm::NW; ++k) { m_abs = fmaxf(m_abs, red_a[k]); m_frob = fmaxf(m_frob, red_f[k]); }
+            // non-negative floats order like their bit patterns
+            atomicMax((unsigned long long*)&p.hstats[NB200_HS_MAX_ABS_BITS], (unsigned long long)nb::f2u(m_abs));
+            atomicMax((unsigned long long*)&p.hstats[NB200_HS_MAX_FROBSQ_BITS], (unsigned long long)nb::f2u(m_frob));
+        }
+    }
+};
+
+// test/diagnostic epilogue: writes the six second derivatives (order zz, zy, zx, yy, yx, xx) as six volumes
+struct DumpParams {
+    float* out;          // 6 x nz_buf x ny x nx
+};
+struct DumpEpi {
+    const DumpParams& p;
+    const nb200_vol& v;
+    __device__ DumpEpi(const DumpParams& p_, const nb200_vol& v_, int, int) : p(p_), v(v_) {}
+    __device__ __forceinline__ void plane(int) {}
+    __device__ __forceinline__ bool skip4(int, int, int, int, int) { return false; }
+    __device__ __forceinline__ void voxels4(int, int zb, int y, int x, int nvalid, const Hess4& h) {
+        const long long vol = (long long)v.nz_buf * v.ny * v.nx;
+        const long long idx = ((long long)zb * v.ny + y) * v.nx + x;
+        const float* c[6] = {&h.zz.x, &h.zy.x, &h.zx.x, &h.yy.x, &h.yx.x, &h.xx.x};
+        for (int j = 0; j < 6; ++j)
+            for (int k = 0; k < 4; ++k)
+                if (k < nvalid) p.out[j * vol + idx + k] = c[j][k];
+    }
+    __device__ void finish() {}
+};
+
+// one out-of-line copy of the eigen-solver + vesselness (keeps the marching loop inside the I-cache)
+__device__ __noinline__ float eig_vesselness(float a00, float a01, float a02, float a11, float a12, float a22,
+                                             float alpha_sq, float beta_sq, float gamma_sq) {
+    float l1, l2, l3;
+    nb::eig3_sym<2>(a00, a01, a02, a11, a12, a22, l1, l2, l3);
+    return nb::vesselness3(l1, l2, l3, alpha_sq, beta_sq, gamma_sq);
+}
+
+struct FrangiParams {
+    float* acc;
+    float alpha_sq, beta_sq;
+    const double* spd;
+    int acc_vec_ok;
+};
+
+struct FrangiEpi {
+    const FrangiParams& p;
+    const nb200_vol& v;
+    float gamma_sq, frob_cut, max_abs;
+    long long plane_sz;
+    float prev[4];
+    long long idx;
+    __device__ FrangiEpi(const FrangiParams& p_, const nb200_vol& v_, int, int) : p(p_), v(v_) {
+        gamma_sq = (float)p.spd[NB200_SP_GAMMA_SQ];
+        frob_cut = (float)p.spd[NB200_SP_FROB_CUT];
+        max_abs = (float)p.spd[NB200_SP_MAX_ABS];
+        plane_sz = (long long)v.ny * v.nx;
+    }
+    __device__ __forceinline__ void plane(int) {}
+    __device__ __forceinline__ bool skip4(int, int zb, int y, int x, int nvalid) {
+        idx = (long long)zb * plane_sz + (long long)y * v.nx + x;
+        if (nvalid == 4 && p.acc_vec_ok) {
+            const float4 a = *reinterpret_cast<const float4*>(p.acc + idx);
+            prev[0] = a.x; prev[1] = a.y; prev[2] = a.z; prev[3] = a.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) prev[k] = k < nvalid ? p.acc[idx + k] : -1.0f;
+        }
+        // dead voxels stay dead whatever this sigma says (AND of masks): skip their Hessian
+        return prev[0] < 0.0f && prev[1] < 0.0f && prev[2] < 0.0f && prev[3] < 0.0f;
+    }
+    __device__ __forceinline__ void voxels4(int, int, int, int, int nvalid, const Hess4& h) {
+        const float* zz = &h.zz.x; const float* zy = &h.zy.x; const float* zx = &h.zx.x;
+        const float* yy = &h.yy.x; const float* yx = &h.yx.x; const float* xx = &h.xx.x;
+        float out[4];
+        const float4 fs4 = frob_sq4(h);
+        const float* fs = &fs4.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            out[k] = prev[k];
+            if (k < nvalid && prev[k] >= 0.0f) {
+                const float frob = sqrtf(fs[k]) / max_abs;
+                if (!(frob > frob_cut)) {
+                    out[k] = -1.0f;
+                } else {
+                    const float vv = eig_vesselness(zz[k], zy[k], zx[k], yy[k], yx[k], xx[k], p.alpha_sq, p.beta_sq, gamma_sq);
+                    if (vv > prev[k]) out[k] = vv;
+                }
             }
         }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        m_abs = fmaxf(m_abs, __shfl_xor_sync(0xffffffffu, m_abs, o));
-        m_frob = fmaxf(m_frob, __shfl_xor_sync(0xffffffffu, m_frob, o));
-    }
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { red_a[w] = m_abs; red_f[w] = m_frob; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < NTHREADS / 32; ++k) { m_abs = fmaxf(m_abs, red_a[k]); m_frob = fmaxf(m_frob, red_f[k]); }
-        // non-negative floats order like their bit patterns
-        atomicMax((unsigned long long*)&hstats[NB200_HS_MAX_ABS_BITS], (unsigned long long)nb::f2u(m_abs));
-        atomicMax((unsigned long long*)&hstats[NB200_HS_MAX_FROBSQ_BITS], (unsigned long long)nb::f2u(m_frob));
-    }
-}
-
-// --------------------------------------------------------------------------------------------
-// K3: fused Hessian + mask + eig + vesselness + accumulate
-// --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS)
-frangi_accumulate_kernel(const float* __restrict__ g, float* __restrict__ acc, nb200_vol v, nb::Spacing3 sp,
-                         float alpha_sq, float beta_sq, const double* __restrict__ spd) {
-    __shared__ Tile tile;
-    if (spd[NB200_SP_SKIP] != 0.0) return;        // empty mask: the sigma contributes nothing (:843-844)
-    const float gamma_sq = (float)spd[NB200_SP_GAMMA_SQ];
-    const float frob_cut = (float)spd[NB200_SP_FROB_CUT];
-    const float max_abs = (float)spd[NB200_SP_MAX_ABS];
-    int zb0, y0, x0; bool valid;
-    brick_origin(v, zb0, y0, x0, valid);
-    load_tile(tile, g, v, zb0, y0, x0);
-    __syncthreads();
-    const int n[3] = {v.nz_glob, v.ny, v.nx};
-    const long long plane = (long long)v.ny * v.nx;
-    const int tx = threadIdx.x % TX, ty0 = threadIdx.x / TX;
-    for (int lz = 0; lz < TZ; ++lz) {
-        const int zb = zb0 + lz;
-        if (zb >= v.zc1) break;
-        const int zg = zb + v.zg_off;
-        for (int ly = ty0; ly < TY; ly += NTHREADS / TX) {
-            const int y = y0 + ly, x = x0 + tx;
-            if (y >= v.ny || x >= v.nx) continue;
-            const long long idx = (long long)zb * plane + (long long)y * v.nx + x;
-            const float prev = acc[idx];
-            if (prev < 0.0f) continue;            // already dead: output is 0 whatever this sigma says
-            TileLoad L{&tile, lz + HALO, ly + HALO, tx + HALO};
-            float a, b, c, d, e, f;
-            nb::hessian3(L, zg, y, x, n, sp, a, b, c, d, e, f);
-            const float frob = sqrtf(nb::frob_sq3(a, b, c, d, e, f)) / max_abs;
-            if (!(frob > frob_cut)) { acc[idx] = -1.0f; continue; }
-            float l1, l2, l3;
-            nb::eig3_sym<2>(a, b, c, d, e, f, l1, l2, l3);
-            const float vv = nb::vesselness3(l1, l2, l3, alpha_sq, beta_sq, gamma_sq);
-            if (vv > prev) acc[idx] = vv;
+        if (nvalid == 4 && p.acc_vec_ok) {
+            *reinterpret_cast<float4*>(p.acc + idx) = make_float4(out[0], out[1], out[2], out[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k < nvalid) p.acc[idx + k] = out[k];
         }
     }
+    __device__ void finish() {}
+};
+
+// --------------------------------------------------------------------------------------------
+// kernel wrapper: tile decode, division-mode / edge dispatch
+// --------------------------------------------------------------------------------------------
+template <int MODE, class Epi, class Params>
+__global__ void __launch_bounds__(hm::NT, 2)
+march_kernel(const float* __restrict__ g, nb200_vol v, hm::Divs dv, const double* __restrict__ flags, int run_if_unsafe,
+             int zchunk, int check_skip, Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    hm::Smem& s = *reinterpret_cast<hm::Smem*>(smem_raw);
+    if (flags != nullptr) {
+        if (check_skip && flags[NB200_SP_SKIP] != 0.0) return;   // empty mask: the sigma contributes nothing (:843-844)
+        // the fast-division launch and its IEEE twin are both enqueued; exactly one of them does the work
+        const bool unsafe = flags[NB200_SP_UNSAFE] != 0.0;
+        if (run_if_unsafe >= 0 && unsafe != (run_if_unsafe != 0)) return;
+    }
+    const int ntx = (v.nx + hm::TX - 1) / hm::TX, nty = (v.ny + hm::TY - 1) / hm::TY;
+    long long b = blockIdx.x;
+    const int bx = (int)(b % ntx); b /= ntx;
+    const int by = (int)(b % nty); b /= nty;
+    hm::Geo q;
+    q.v = v;
+    q.x0 = bx * hm::TX;
+    q.y0 = by * hm::TY;
+    q.plane = (long long)v.ny * v.nx;
+    q.vec_ok = (q.x0 + hm::TX <= v.nx) && (v.nx % 4 == 0) && ((reinterpret_cast<unsigned long long>(g) & 15ull) == 0);
+    const int zs = v.zc0 + v.zg_off + (int)b * zchunk;               // global planes
+    const int ze = min(zs + zchunk, v.zc1 + v.zg_off);
+    if (zs >= ze) return;
+    Epi epi(p, v, q.x0, q.y0);
+    const bool edge = q.x0 < 2 || q.x0 + hm::TX + 2 > v.nx || q.y0 < 2 || q.y0 + hm::TY + 2 > v.ny;
+    if (edge) hm::march<MODE, true>(s, g, q, dv, zs, ze, epi);
+    else hm::march<MODE, false>(s, g, q, dv, zs, ze, epi);
+    epi.finish();
+}
+
+// exhaustive check of the reciprocal-multiply division against IEEE division for one divisor:
+// every numerator with exponent in [-90, 90] plus +-0 (the range the FAST path is allowed to see)
+__global__ void __launch_bounds__(256)
+verify_divisor_kernel(float d, float r, unsigned long long* __restrict__ mismatches) {
+    unsigned long long bad = 0;
+    const unsigned lo_e = 127 - 90, hi_e = 127 + 90;
+    const unsigned long long total = (unsigned long long)(hi_e - lo_e + 1) << 24;   // exponent x sign x mantissa
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned mant = (unsigned)(i & 0x7fffffu);
+        const unsigned sign = (unsigned)((i >> 23) & 1u);
+        const unsigned e = lo_e + (unsigned)(i >> 24);
+        const float n = nb::u2f((sign << 31) | (e << 23) | mant);
+        const float a = hm::divc<hm::DIV_FAST>(n, d, r);
+        const float b = n / d;
+        bad += (nb::f2u(a) != nb::f2u(b)) ? 1 : 0;
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        // +0 must map to +0.  (-0 maps to +0 instead of -0: the sign of a zero never reaches a result —
+        // Hessian entries are squared, compared by magnitude, or added to non-zero terms.)
+        const float z0 = hm::divc<hm::DIV_FAST>(0.0f, d, r), z1 = hm::divc<hm::DIV_FAST>(-0.0f, d, r);
+        bad += (nb::f2u(z0) != nb::f2u(0.0f / d)) + (z1 != 0.0f);
+    }
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(mismatches, bad);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -240,15 +351,71 @@ int check_vol(const nb200_vol& v, const char* who) {
     return NB200_OK;
 }
 
-unsigned brick_grid(const nb200_vol& v) {
-    const long long nbx = (v.nx + TX - 1) / TX, nby = (v.ny + TY - 1) / TY, nbz = (v.zc1 - v.zc0 + TZ - 1) / TZ;
-    return (unsigned)(nbx * nby * nbz);
+// Z chunk length: enough CTAs for a few waves (2 CTAs/SM), chunks no shorter than 8 planes
+int pick_zchunk(const nb200_vol& v, long long* n_ctas) {
+    const long long tiles = (long long)((v.nx + hm::TX - 1) / hm::TX) * ((v.ny + hm::TY - 1) / hm::TY);
+    const int nz = v.zc1 - v.zc0;
+    const long long want = 8LL * nb::sm_count();
+    long long chunks = (want + tiles - 1) / tiles;
+    if (chunks < 1) chunks = 1;
+    int zchunk = (int)((nz + chunks - 1) / chunks);
+    if (zchunk < 8) zchunk = nz < 8 ? nz : 8;
+    chunks = (nz + zchunk - 1) / zchunk;
+    *n_ctas = tiles * chunks;
+    return zchunk;
 }
 
-nb::Spacing3 spacing_from(const float* s) {
-    nb::Spacing3 sp;
-    for (int a = 0; a < 3; ++a) { sp.h1[a] = s[2 * a]; sp.h2[a] = s[2 * a + 1]; }
-    return sp;
+hm::Divs divs_from(const float* s) {
+    hm::Divs dv;
+    for (int a = 0; a < 3; ++a) {
+        dv.a[a].d1 = s[2 * a];
+        dv.a[a].r1 = 1.0f / s[2 * a];
+        dv.a[a].d2 = s[2 * a + 1];
+        dv.a[a].r2 = 1.0f / s[2 * a + 1];
+    }
+    return dv;
+}
+
+template <class K>
+int set_smem(K kernel) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(hm::Smem));
+    if (e != cudaSuccess) {
+        nb::set_error("cudaFuncSetAttribute(smem=%zu): %s", sizeof(hm::Smem), cudaGetErrorString(e));
+        return NB200_ERR_CUDA;
+    }
+    return NB200_OK;
+}
+
+template <int MODE, class Epi, class Params>
+int launch_one(const float* g, const nb200_vol& v, const float* spacing, const double* sp, int run_if_unsafe,
+               int check_skip, const Params& p, cudaStream_t st) {
+    auto kernel = march_kernel<MODE, Epi, Params>;
+    static bool smem_set = false;       // one flag per <MODE, Epi> instantiation
+    if (!smem_set) {
+        int rc = set_smem(kernel);
+        if (rc) return rc;
+        smem_set = true;
+    }
+    long long n_ctas = 0;
+    const int zchunk = pick_zchunk(v, &n_ctas);
+    kernel<<<(unsigned)n_ctas, hm::NT, sizeof(hm::Smem), st>>>(g, v, divs_from(spacing), sp, run_if_unsafe, zchunk,
+                                                                check_skip, p);
+    return NB200_OK;
+}
+
+// FAST mode enqueues the fast kernel and its IEEE twin; the device flag sp[UNSAFE] picks the one that runs
+template <class Epi, class Params>
+int launch_march(const float* g, const nb200_vol& v, const float* spacing, int div_mode, const double* sp,
+                 int check_skip, const Params& p, cudaStream_t st, const char* what) {
+    int rc;
+    if (div_mode == hm::DIV_POW2) rc = launch_one<hm::DIV_POW2, Epi>(g, v, spacing, sp, -1, check_skip, p, st);
+    else if (div_mode == hm::DIV_IEEE || sp == nullptr) rc = launch_one<hm::DIV_IEEE, Epi>(g, v, spacing, sp, -1, check_skip, p, st);
+    else {
+        rc = launch_one<hm::DIV_FAST, Epi>(g, v, spacing, sp, 0, check_skip, p, st);
+        if (rc == NB200_OK) rc = launch_one<hm::DIV_IEEE, Epi>(g, v, spacing, sp, 1, check_skip, p, st);
+    }
+    if (rc) return rc;
+    return nb::check_launch(what);
 }
 
 }  // namespace
@@ -261,32 +428,79 @@ int nb200_hstats_reset(long long* hstats, void* stream) {
     return nb::check_launch("hstats_reset");
 }
 
-int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* spacing, int sz, int sy, int sx,
-                        float* frob_samples, long long* hstats, void* stream) {
+int nb200_divisor_mode(float d, int* mode_out, void* stream) {
+    NB_REQUIRE(mode_out && d > 0.0f && d < INFINITY, NB200_ERR_ARG, "nb200_divisor_mode: bad divisor");
+    int e = 0;
+    const float m = frexpf(d, &e);
+    if (m == 0.5f && e > -60 && e < 60) { *mode_out = hm::DIV_POW2; return NB200_OK; }
+    cudaStream_t st = nb::as_stream(stream);
+    unsigned long long* dev = nullptr;
+    cudaError_t ce = cudaMalloc(&dev, sizeof(unsigned long long));   // init-time only, never on the frame path
+    NB_REQUIRE(ce == cudaSuccess, NB200_ERR_OOM, "nb200_divisor_mode: out of memory");
+    cudaMemsetAsync(dev, 0, sizeof(unsigned long long), st);
+    verify_divisor_kernel<<<nb::sm_count() * 8, 256, 0, st>>>(d, 1.0f / d, dev);
+    unsigned long long bad = 1;
+    ce = cudaMemcpyAsync(&bad, dev, sizeof(bad), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    NB_REQUIRE(ce == cudaSuccess, NB200_ERR_CUDA, "nb200_divisor_mode: %s", cudaGetErrorString(ce));
+    *mode_out = bad == 0 ? hm::DIV_FAST : hm::DIV_IEEE;
+    return NB200_OK;
+}
+
+int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode, const double* sp,
+                        int sz, int sy, int sx, float* frob_samples, long long* hstats, void* stream) {
     NB_REQUIRE(gauss && vol && spacing && hstats && sz > 0 && sy > 0 && sx > 0, NB200_ERR_ARG,
                "nb200_hessian_stats: bad argument");
+    NB_REQUIRE(div_mode >= 0 && div_mode <= 2, NB200_ERR_ARG, "nb200_hessian_stats: div_mode %d", div_mode);
     const nb200_vol v = *vol;
     int rc = check_vol(v, "nb200_hessian_stats");
     if (rc) return rc;
     if (v.zc0 == v.zc1) return NB200_OK;
+    StatsParams p;
+    p.sz = sz; p.sy = sy; p.sx = sx;
     const int g0 = v.zc0 + v.zg_off;
-    const int g_first = ((g0 + sz - 1) / sz) * sz;
-    const int ly_n = (v.ny + sy - 1) / sy, lx_n = (v.nx + sx - 1) / sx;
-    hessian_stats_kernel<<<brick_grid(v), NTHREADS, 0, nb::as_stream(stream)>>>(
-        gauss, v, spacing_from(spacing), sz, sy, sx, g_first, ly_n, lx_n, frob_samples, hstats);
-    return nb::check_launch("hessian_stats");
+    p.g_first = ((g0 + sz - 1) / sz) * sz;
+    p.ly_n = (v.ny + sy - 1) / sy;
+    p.lx_n = (v.nx + sx - 1) / sx;
+    p.frob_samples = frob_samples;
+    p.hstats = hstats;
+    return launch_march<StatsEpi>(gauss, v, spacing, div_mode, sp, 0, p, nb::as_stream(stream), "hessian_stats");
 }
 
-int nb200_frangi_accumulate(const float* gauss, float* acc, const nb200_vol* vol, const float* spacing,
+int nb200_hessian_components(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode, float* out6,
+                             void* stream) {
+    NB_REQUIRE(gauss && vol && spacing && out6, NB200_ERR_ARG, "nb200_hessian_components: null argument");
+    NB_REQUIRE(div_mode >= 0 && div_mode <= 2, NB200_ERR_ARG, "nb200_hessian_components: div_mode %d", div_mode);
+    const nb200_vol v = *vol;
+    int rc = check_vol(v, "nb200_hessian_components");
+    if (rc) return rc;
+    if (v.zc0 == v.zc1) return NB200_OK;
+    DumpParams p;
+    p.out = out6;
+    cudaStream_t st = nb::as_stream(stream);
+    if (div_mode == hm::DIV_POW2) rc = launch_one<hm::DIV_POW2, DumpEpi>(gauss, v, spacing, nullptr, -1, 0, p, st);
+    else if (div_mode == hm::DIV_FAST) rc = launch_one<hm::DIV_FAST, DumpEpi>(gauss, v, spacing, nullptr, -1, 0, p, st);
+    else rc = launch_one<hm::DIV_IEEE, DumpEpi>(gauss, v, spacing, nullptr, -1, 0, p, st);
+    if (rc) return rc;
+    return nb::check_launch("hessian_components");
+}
+
+int nb200_frangi_accumulate(const float* gauss, float* acc, const nb200_vol* vol, const float* spacing, int div_mode,
                             float alpha_sq, float beta_sq, const double* sp, void* stream) {
     NB_REQUIRE(gauss && acc && vol && spacing && sp, NB200_ERR_ARG, "nb200_frangi_accumulate: null argument");
+    NB_REQUIRE(div_mode >= 0 && div_mode <= 2, NB200_ERR_ARG, "nb200_frangi_accumulate: div_mode %d", div_mode);
     const nb200_vol v = *vol;
     int rc = check_vol(v, "nb200_frangi_accumulate");
     if (rc) return rc;
     if (v.zc0 == v.zc1) return NB200_OK;
-    frangi_accumulate_kernel<<<brick_grid(v), NTHREADS, 0, nb::as_stream(stream)>>>(
-        gauss, acc, v, spacing_from(spacing), alpha_sq, beta_sq, sp);
-    return nb::check_launch("frangi_accumulate");
+    FrangiParams p;
+    p.acc = acc;
+    p.alpha_sq = alpha_sq;
+    p.beta_sq = beta_sq;
+    p.spd = sp;
+    p.acc_vec_ok = (v.nx % 4 == 0) && ((reinterpret_cast<unsigned long long>(acc) & 15ull) == 0);
+    return launch_march<FrangiEpi>(gauss, v, spacing, div_mode, sp, 1, p, nb::as_stream(stream), "frangi_accumulate");
 }
 
 int nb200_hessian_stats_2d(const float* gauss, int ny, int nx, const float* spacing, int sy, int sx,

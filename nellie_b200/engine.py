@@ -111,6 +111,9 @@ def gaussian_taps(delta_sigma: float, truncate: float):
     return np.ascontiguousarray(phi[radius:], dtype=np.float64), radius
 
 
+_DIV_MODE_CACHE = {}
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -178,6 +181,7 @@ class FrangiEngine3D:
         self.pct = torch.zeros(2, dtype=torch.float64, device=dev)
         self.fd = params.fd_spacing_f32()
         self._fd_c = self.fd.ctypes.data_as(C.POINTER(C.c_float))
+        self.div_mode = self._pick_div_mode()
         self.launches = 0
         self.profile = None   # set to a list to record (name, start, end) CUDA events per C-ABI call
         # hooks for the multi-GPU driver (identity on one GPU)
@@ -186,6 +190,23 @@ class FrangiEngine3D:
         self.reduce_hist_bins = lambda state: None
         self.reduce_hstats = lambda hs: None
         self.gather_samples = lambda s, n: (s, n)
+
+    def _pick_div_mode(self):
+        """Weakest division mode over the six grid-spacing divisors (verified on the device, once)."""
+        modes = []
+        with torch.cuda.device(self.device):
+            for d in self.fd:
+                key = float(d)
+                if key not in _DIV_MODE_CACHE:
+                    m = C.c_int(0)
+                    _cabi.check(self.lib.nb200_divisor_mode(C.c_float(key), C.byref(m), _stream()), "nb200_divisor_mode")
+                    _DIV_MODE_CACHE[key] = int(m.value)
+                modes.append(_DIV_MODE_CACHE[key])
+        if all(m == _cabi.DIV_POW2 for m in modes):
+            return _cabi.DIV_POW2
+        if all(m in (_cabi.DIV_POW2, _cabi.DIV_FAST) for m in modes):
+            return _cabi.DIV_FAST
+        return _cabi.DIV_IEEE
 
     # -- geometry helpers ---------------------------------------------------------------------
     def vol(self, extra_lo=0, extra_hi=0) -> Vol:
@@ -262,8 +283,8 @@ class FrangiEngine3D:
             self._call("nb200_finalize_gamma", _ptr(self.hist), _ptr(sp_i), st)
             # F4: Hessian statistics (max|H|, max frob^2, frob samples)
             self._call("nb200_hstats_reset", _ptr(self.hstats), st)
-            self._call("nb200_hessian_stats", _ptr(g), C.byref(own), self._fd_c, sz, sy, sx,
-                       _ptr(self.samples), _ptr(self.hstats), st)
+            self._call("nb200_hessian_stats", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
+                       sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), st)
             self.reduce_hstats(self.hstats)
             self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
             # F5: Frobenius threshold
@@ -276,7 +297,7 @@ class FrangiEngine3D:
                 self._call("nb200_hist_reset", _ptr(self.hist), st)
             self._call("nb200_finalize_frob", _ptr(self.hist), _ptr(self.hstats), fixed, division, _ptr(sp_i), st)
             # F4-F9 fused
-            self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c,
+            self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode,
                        float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
 
     def finalize(self, apply_mask_volume=True):
