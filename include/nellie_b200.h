@@ -72,6 +72,7 @@ typedef struct nb200_vol {
 #define NB200_SP_OTSU 8
 #define NB200_SP_UNSAFE 9     /* 1.0 when the blurred volume holds values outside the exponent range the fast
                                  constant-divisor division was verified on: kernels fall back to IEEE division */
+#define NB200_SP_FROBSQ_MIN 10 /* smallest frob_sq whose sqrt(.)/max_abs exceeds fl32(cut): mask = frob_sq >= this */
 #define NB200_SP_WORDS 12
 
 /* int64[NB200_HS_WORDS] device record reduced by nb200_hessian_stats */

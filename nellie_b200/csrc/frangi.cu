@@ -12,6 +12,8 @@
 // Both kernels are epilogues of the Z-marching Hessian in hessian_march.cuh (shared-memory ring of
 // blurred planes fed by cp.async, first-derivative planes shared between the second derivatives,
 // 4 voxels per thread with 128-bit shared/global accesses).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "hessian.cuh"
 #include "hessian_march.cuh"
@@ -59,7 +61,7 @@ struct StatsEpi {
     int xmask = 0, xlat = 0;            // lattice columns inside this thread's 4-voxel group (loop invariant)
     int ylat[hm::TY / hm::NW];          // lattice row index of each output row, or -1
     long long zrow = -1;                // lattice plane offset of the current plane, or -1 (uniform)
-    __device__ StatsEpi(const StatsParams& p_, const nb200_vol& v_, int x0, int y0) : p(p_), v(v_) {
+    __device__ StatsEpi(const StatsParams& p_, const nb200_vol& v_, int x0, int y0, void*) : p(p_), v(v_) {
         const int x = x0 + 4 * (threadIdx.x & 31);
         for (int k = 0; k < 4; ++k) xmask |= ((x + k) % p.sx == 0) ? (1 << k) : 0;
         xlat = (x + p.sx - 1) / p.sx;
@@ -71,8 +73,10 @@ struct StatsEpi {
     __device__ __forceinline__ void plane(int zg) {
         zrow = (zg % p.sz == 0) ? (long long)((zg - p.g_first) / p.sz) * p.ly_n : -1;
     }
+    __device__ __forceinline__ void preload(int, int, int, int, int) {}
     __device__ __forceinline__ bool skip4(int, int, int, int, int) { return false; }
-    __device__ __forceinline__ void voxels4(int row, int, int, int x, int nvalid, const Hess4& h) {
+    __device__ __forceinline__ void voxels4(int row, bool active, int, int, int x, int nvalid, const Hess4& h) {
+        if (!active) return;
         const float4 fs = frob_sq4(h);
         if (nvalid == 4) {
             m_abs = fmaxf(m_abs, fmaxf(fmaxf(fmaxf(absmax4(h.zz), absmax4(h.zy)), fmaxf(absmax4(h.zx), absmax4(h.yy))),
@@ -122,10 +126,12 @@ struct DumpParams {
 struct DumpEpi {
     const DumpParams& p;
     const nb200_vol& v;
-    __device__ DumpEpi(const DumpParams& p_, const nb200_vol& v_, int, int) : p(p_), v(v_) {}
+    __device__ DumpEpi(const DumpParams& p_, const nb200_vol& v_, int, int, void*) : p(p_), v(v_) {}
     __device__ __forceinline__ void plane(int) {}
+    __device__ __forceinline__ void preload(int, int, int, int, int) {}
     __device__ __forceinline__ bool skip4(int, int, int, int, int) { return false; }
-    __device__ __forceinline__ void voxels4(int, int zb, int y, int x, int nvalid, const Hess4& h) {
+    __device__ __forceinline__ void voxels4(int, bool active, int zb, int y, int x, int nvalid, const Hess4& h) {
+        if (!active) return;
         const long long vol = (long long)v.nz_buf * v.ny * v.nx;
         const long long idx = ((long long)zb * v.ny + y) * v.nx + x;
         const float* c[6] = {&h.zz.x, &h.zy.x, &h.zx.x, &h.yy.x, &h.yx.x, &h.xx.x};
@@ -141,7 +147,23 @@ __device__ __noinline__ float eig_vesselness(float a00, float a01, float a02, fl
                                              float alpha_sq, float beta_sq, float gamma_sq) {
     float l1, l2, l3;
     nb::eig3_sym<2>(a00, a01, a02, a11, a12, a22, l1, l2, l3);
+    if (l3 > 0.0f || l2 > 0.0f) return 0.0f;           // filtering.py:759-761 zeroes these responses
     return nb::vesselness3(l1, l2, l3, alpha_sq, beta_sq, gamma_sq);
+}
+
+// two independent voxels per call: the long float64 dependency chains of the two solves interleave (ILP 2)
+struct H6 {
+    float a00, a01, a02, a11, a12, a22;
+};
+__device__ __noinline__ float2 eig_vesselness_pair(H6 a, H6 b, float alpha_sq, float beta_sq, float gamma_sq) {
+    float l1, l2, l3, m1, m2, m3;
+    nb::eig3_sym<2>(a.a00, a.a01, a.a02, a.a11, a.a12, a.a22, l1, l2, l3);
+    nb::eig3_sym<2>(b.a00, b.a01, b.a02, b.a11, b.a12, b.a22, m1, m2, m3);
+    float2 r = make_float2(0.0f, 0.0f);
+    const bool need_a = !(l3 > 0.0f || l2 > 0.0f), need_b = !(m3 > 0.0f || m2 > 0.0f);   // filtering.py:759-761
+    if (need_a) r.x = nb::vesselness3(l1, l2, l3, alpha_sq, beta_sq, gamma_sq);
+    if (need_b) r.y = nb::vesselness3(m1, m2, m3, alpha_sq, beta_sq, gamma_sq);
+    return r;
 }
 
 struct FrangiParams {
@@ -149,62 +171,135 @@ struct FrangiParams {
     float alpha_sq, beta_sq;
     const double* spd;
     int acc_vec_ok;
+    int debug;        // profiling experiments only (NB200_K3_DEBUG): 1 = skip the solves, 2 = eigenvalues only
+};
+
+// Per-warp work queue in shared memory.  The Hessian phase is dense (every live voxel), but only the
+// voxels that pass the Frobenius mask need eigenvalues + vesselness (a few hundred instructions with
+// float64 Newton steps): they are pushed here and popped 32 at a time, so that expensive part always
+// runs with full warps instead of diverging on the speckled mask.
+constexpr int QCAP = 96;      // entries per warp: < 64 left over + <= 32 pushed per round
+constexpr int QWORDS = 7;     // six second derivatives + voxel index
+struct FrangiQueue {
+    float w[hm::NW][QWORDS][QCAP];
 };
 
 struct FrangiEpi {
     const FrangiParams& p;
     const nb200_vol& v;
-    float gamma_sq, frob_cut, max_abs;
+    float gamma_sq, fs_min;
     long long plane_sz;
-    float prev[4];
-    long long idx;
-    __device__ FrangiEpi(const FrangiParams& p_, const nb200_vol& v_, int, int) : p(p_), v(v_) {
+    float prev_[hm::TY / hm::NW][4];       // accumulator values of this thread's groups, one set per output row
+    float next_[hm::TY / hm::NW][4];       // ... of the next plane, in flight
+    long long idx_[hm::TY / hm::NW];
+    float (*q)[QCAP];          // this warp's queue: q[word][entry]
+    int fill = 0;              // warp-uniform
+    int lane;
+    __device__ FrangiEpi(const FrangiParams& p_, const nb200_vol& v_, int, int, void* queue_mem) : p(p_), v(v_) {
         gamma_sq = (float)p.spd[NB200_SP_GAMMA_SQ];
-        frob_cut = (float)p.spd[NB200_SP_FROB_CUT];
-        max_abs = (float)p.spd[NB200_SP_MAX_ABS];
+        fs_min = (float)p.spd[NB200_SP_FROBSQ_MIN];    // mask <=> frob_sq >= fs_min (see finalize_frob_kernel)
         plane_sz = (long long)v.ny * v.nx;
+        q = reinterpret_cast<FrangiQueue*>(queue_mem)->w[threadIdx.x >> 5];
+        lane = threadIdx.x & 31;
     }
     __device__ __forceinline__ void plane(int) {}
-    __device__ __forceinline__ bool skip4(int, int zb, int y, int x, int nvalid) {
-        idx = (long long)zb * plane_sz + (long long)y * v.nx + x;
+    // accumulator values of plane zb are requested one iteration ahead (preload) and consumed by skip4
+    __device__ __forceinline__ void preload(int row, int zb, int y, int x, int nvalid) {
+        float* nxt = next_[row];
+        const long long idx = (long long)zb * plane_sz + (long long)y * v.nx + x;
         if (nvalid == 4 && p.acc_vec_ok) {
             const float4 a = *reinterpret_cast<const float4*>(p.acc + idx);
-            prev[0] = a.x; prev[1] = a.y; prev[2] = a.z; prev[3] = a.w;
+            nxt[0] = a.x; nxt[1] = a.y; nxt[2] = a.z; nxt[3] = a.w;
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) prev[k] = k < nvalid ? p.acc[idx + k] : -1.0f;
+            for (int k = 0; k < 4; ++k) nxt[k] = k < nvalid ? p.acc[idx + k] : -1.0f;
         }
+    }
+    __device__ __forceinline__ bool skip4(int row, int zb, int y, int x, int) {
+        float* prev = prev_[row];
+        idx_[row] = (long long)zb * plane_sz + (long long)y * v.nx + x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) prev[k] = next_[row][k];
         // dead voxels stay dead whatever this sigma says (AND of masks): skip their Hessian
         return prev[0] < 0.0f && prev[1] < 0.0f && prev[2] < 0.0f && prev[3] < 0.0f;
     }
-    __device__ __forceinline__ void voxels4(int, int, int, int, int nvalid, const Hess4& h) {
-        const float* zz = &h.zz.x; const float* zy = &h.zy.x; const float* zx = &h.zx.x;
-        const float* yy = &h.yy.x; const float* yx = &h.yx.x; const float* xx = &h.xx.x;
-        float out[4];
-        const float4 fs4 = frob_sq4(h);
-        const float* fs = &fs4.x;
+    // pop `n` entries (n <= 64) from the top of the queue: two entries per lane, dense
+    __device__ __forceinline__ void drain(int n) {
+        __syncwarp();
+        const int base = fill - n;
+        const bool has_a = lane < n, has_b = lane + 32 < n;
+        if (has_a) {
+            const int ea = base + lane, eb = has_b ? ea + 32 : ea;
+            H6 a, b;
+            a.a00 = q[0][ea]; a.a01 = q[1][ea]; a.a02 = q[2][ea]; a.a11 = q[3][ea]; a.a12 = q[4][ea]; a.a22 = q[5][ea];
+            b.a00 = q[0][eb]; b.a01 = q[1][eb]; b.a02 = q[2][eb]; b.a11 = q[3][eb]; b.a12 = q[4][eb]; b.a22 = q[5][eb];
+            const int at_a = __float_as_int(q[6][ea]), at_b = __float_as_int(q[6][eb]);
+            const float cur_a = p.acc[at_a], cur_b = p.acc[at_b];      // issued before the solves: latency hidden
+            float2 vv = make_float2(0.0f, 0.0f);
+            if (p.debug == 0) vv = eig_vesselness_pair(a, b, p.alpha_sq, p.beta_sq, gamma_sq);
+            else if (p.debug == 2) {
+                float l1, l2, l3, m1, m2, m3;
+                nb::eig3_sym<2>(a.a00, a.a01, a.a02, a.a11, a.a12, a.a22, l1, l2, l3);
+                nb::eig3_sym<2>(b.a00, b.a01, b.a02, b.a11, b.a12, b.a22, m1, m2, m3);
+                vv = make_float2(fabsf(l3) * 1e-30f, fabsf(m3) * 1e-30f);
+            }
+            if (vv.x > cur_a) p.acc[at_a] = vv.x;                      // acc >= 0 here: a zero response changes nothing
+            if (has_b && vv.y > cur_b) p.acc[at_b] = vv.y;
+        }
+        fill -= n;
+        __syncwarp();
+    }
+    // called by ALL lanes of the warp (active = this lane has a group with a fresh Hessian)
+    __device__ __forceinline__ void voxels4(int row, bool active, int, int, int, int nvalid, const Hess4& h) {
+        const float* prev = prev_[row];
+        const long long idx = idx_[row];
+        bool pass[4] = {false, false, false, false};
+        if (active) {
+            const float4 fs4 = frob_sq4(h);
+            const float* fs = &fs4.x;
+            float out[4];
+            bool killed = false;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            out[k] = prev[k];
-            if (k < nvalid && prev[k] >= 0.0f) {
-                const float frob = sqrtf(fs[k]) / max_abs;
-                if (!(frob > frob_cut)) {
-                    out[k] = -1.0f;
+            for (int k = 0; k < 4; ++k) {
+                out[k] = prev[k];
+                const bool alive = k < nvalid && prev[k] >= 0.0f;
+                pass[k] = alive && fs[k] >= fs_min;
+                if (alive && !pass[k]) { out[k] = -1.0f; killed = true; }
+                // A non-zero response needs the two largest-|lambda| eigenvalues <= 0 and the third no larger
+                // in magnitude, hence trace <= 0 (also for the float32-rounded eigenvalues the reference
+                // tests).  A trace that is positive beyond its own rounding error therefore means V = 0:
+                // the voxel stays alive and unchanged, no solve.
+                const float dz = (&h.zz.x)[k], dy = (&h.yy.x)[k], dx = (&h.xx.x)[k];
+                if (pass[k] && (dz + dy) + dx > 2.4e-7f * ((fabsf(dz) + fabsf(dy)) + fabsf(dx))) pass[k] = false;
+            }
+            if (killed) {
+                if (nvalid == 4 && p.acc_vec_ok) {
+                    *reinterpret_cast<float4*>(p.acc + idx) = make_float4(out[0], out[1], out[2], out[3]);
                 } else {
-                    const float vv = eig_vesselness(zz[k], zy[k], zx[k], yy[k], yx[k], xx[k], p.alpha_sq, p.beta_sq, gamma_sq);
-                    if (vv > prev[k]) out[k] = vv;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k < nvalid) p.acc[idx + k] = out[k];
                 }
             }
         }
-        if (nvalid == 4 && p.acc_vec_ok) {
-            *reinterpret_cast<float4*>(p.acc + idx) = make_float4(out[0], out[1], out[2], out[3]);
-        } else {
+        const float* c[6] = {&h.zz.x, &h.zy.x, &h.zx.x, &h.yy.x, &h.yx.x, &h.xx.x};
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k < nvalid) p.acc[idx + k] = out[k];
+        for (int k = 0; k < 4; ++k) {
+            const unsigned bits = __ballot_sync(0xffffffffu, pass[k]);
+            if (bits == 0u) continue;
+            if (pass[k]) {
+                const int e = fill + __popc(bits & ((1u << lane) - 1u));
+#pragma unroll
+                for (int j = 0; j < 6; ++j) q[j][e] = c[j][k];
+                q[6][e] = __int_as_float((int)(idx + k));
+            }
+            fill += __popc(bits);
+            if (fill >= 64) drain(64);
         }
     }
-    __device__ void finish() {}
+    __device__ void finish() {
+        while (fill > 0) drain(fill < 64 ? fill : 64);
+    }
 };
 
 // --------------------------------------------------------------------------------------------
@@ -235,7 +330,7 @@ march_kernel(const float* __restrict__ g, nb200_vol v, hm::Divs dv, const double
     const int zs = v.zc0 + v.zg_off + (int)b * zchunk;               // global planes
     const int ze = min(zs + zchunk, v.zc1 + v.zg_off);
     if (zs >= ze) return;
-    Epi epi(p, v, q.x0, q.y0);
+    Epi epi(p, v, q.x0, q.y0, smem_raw + sizeof(hm::Smem));
     const bool edge = q.x0 < 2 || q.x0 + hm::TX + 2 > v.nx || q.y0 < 2 || q.y0 + hm::TY + 2 > v.ny;
     if (edge) hm::march<MODE, true>(s, g, q, dv, zs, ze, epi);
     else hm::march<MODE, false>(s, g, q, dv, zs, ze, epi);
@@ -376,11 +471,13 @@ hm::Divs divs_from(const float* s) {
     return dv;
 }
 
+constexpr size_t kSmemBytes = sizeof(hm::Smem) + sizeof(FrangiQueue);
+
 template <class K>
 int set_smem(K kernel) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(hm::Smem));
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) {
-        nb::set_error("cudaFuncSetAttribute(smem=%zu): %s", sizeof(hm::Smem), cudaGetErrorString(e));
+        nb::set_error("cudaFuncSetAttribute(smem=%zu): %s", kSmemBytes, cudaGetErrorString(e));
         return NB200_ERR_CUDA;
     }
     return NB200_OK;
@@ -398,7 +495,7 @@ int launch_one(const float* g, const nb200_vol& v, const float* spacing, const d
     }
     long long n_ctas = 0;
     const int zchunk = pick_zchunk(v, &n_ctas);
-    kernel<<<(unsigned)n_ctas, hm::NT, sizeof(hm::Smem), st>>>(g, v, divs_from(spacing), sp, run_if_unsafe, zchunk,
+    kernel<<<(unsigned)n_ctas, hm::NT, kSmemBytes, st>>>(g, v, divs_from(spacing), sp, run_if_unsafe, zchunk,
                                                                 check_skip, p);
     return NB200_OK;
 }
@@ -500,6 +597,10 @@ int nb200_frangi_accumulate(const float* gauss, float* acc, const nb200_vol* vol
     p.beta_sq = beta_sq;
     p.spd = sp;
     p.acc_vec_ok = (v.nx % 4 == 0) && ((reinterpret_cast<unsigned long long>(acc) & 15ull) == 0);
+    {
+        const char* dbg = getenv("NB200_K3_DEBUG");
+        p.debug = dbg ? atoi(dbg) : 0;
+    }
     return launch_march<FrangiEpi>(gauss, v, spacing, div_mode, sp, 1, p, nb::as_stream(stream), "frangi_accumulate");
 }
 

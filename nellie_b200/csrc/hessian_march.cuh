@@ -289,8 +289,9 @@ struct Hess4 {
 
 // The march.  Epi provides:
 //   void plane(int zg);                                            // once per output plane (uniform)
+//   void preload(int row, int zb, int y, int x, int nvalid);       // issue loads the epilogue needs for that plane
 //   bool skip4(int row, int zb, int y, int x, int nvalid);         // true: this group needs no Hessian
-//   void voxels4(int row, int zb, int y, int x, int nvalid, const Hess4&);   // 4 consecutive X outputs
+//   void voxels4(int row, bool active, int zb, int y, int x, int nvalid, const Hess4&);   // called by ALL lanes
 // EDGE = the tile touches the frame border in X or Y or is partial (one-sided rules, bounds checks).
 template <int MODE, bool EDGE, class Epi>
 __device__ __forceinline__ void march(Smem& s, const float* __restrict__ g, const Geo& q, const Divs& dv,
@@ -330,6 +331,9 @@ __device__ __forceinline__ void march(Smem& s, const float* __restrict__ g, cons
     load_g_plane(s, g, q, t, zs - 2);
     load_g_plane(s, g, q, t, zs - 1);
     load_g_plane(s, g, q, t, zs);
+#pragma unroll
+    for (int i = 0; i < TY / NW; ++i)          // epilogue inputs of the first output plane
+        if (!EDGE || nvalid_[i] > 0) epi.preload(i, zs - q.v.zg_off, y_[i], t.x, nvalid_[i]);
     // gz ring: the slot receiving gz(tz+1) advances by one per iteration (no integer division)
     int slot_new = 0;
     for (int tz = zs - 2; tz < ze; ++tz) {
@@ -358,10 +362,20 @@ __device__ __forceinline__ void march(Smem& s, const float* __restrict__ g, cons
             const float* GY = &s.gy[0][0];
             const int zb = tz - q.v.zg_off;
             epi.plane(tz);
+            bool active_[TY / NW];
+#pragma unroll
+            for (int i = 0; i < TY / NW; ++i)      // all accumulator loads first: their latency overlaps the Hessians
+                active_[i] = (!EDGE || nvalid_[i] > 0) && !epi.skip4(i, zb, y_[i], t.x, nvalid_[i]);
+            if (tz + 1 < ze) {                     // next plane's epilogue inputs: a whole iteration to arrive
+#pragma unroll
+                for (int i = 0; i < TY / NW; ++i)
+                    if (!EDGE || nvalid_[i] > 0) epi.preload(i, zb + 1, y_[i], t.x, nvalid_[i]);
+            }
 #pragma unroll
             for (int i = 0; i < TY / NW; ++i) {
-                if ((!EDGE || nvalid_[i] > 0) && !epi.skip4(i, zb, y_[i], t.x, nvalid_[i])) {
-                    Hess4 h;
+                const bool active = active_[i];
+                Hess4 h;
+                if (active) {
                     const int o = off_[i];
                     DivK ky = ds.y2;
                     if (EDGE && yedge_[i]) ky = make_divk(ds.ay.d1, ds.ay.r1);
@@ -371,8 +385,8 @@ __device__ __forceinline__ void march(Smem& s, const float* __restrict__ g, cons
                     h.zx = ddx4<MODE, EDGE>(GZC + o - t.col, t, ds);
                     h.yx = ddx4<MODE, EDGE>(GY + o - t.col, t, ds);
                     h.xx = ddx4<MODE, EDGE>(&s.gx[t.warp + i * NW][0], t, ds);
-                    epi.voxels4(i, zb, y_[i], t.x, nvalid_[i], h);
                 }
+                epi.voxels4(i, active, zb, y_[i], t.x, nvalid_[i], h);   // every lane: epilogues may use warp votes
             }
         }
         slot_new = slot_new == 2 ? 0 : slot_new + 1;

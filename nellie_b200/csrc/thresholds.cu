@@ -289,6 +289,23 @@ __global__ void finalize_frob_kernel(const long long* state, const long long* hs
         cut = thr / division;
     }
     any = top > (float)cut;     // sqrt and division are monotone: max frob decides emptiness
+    // K3 tests frob_sq directly: sqrt and the division by max_abs are monotone, so the mask
+    // "sqrt(fs)/max_abs > cut" is an up-set {fs >= fs_min}; find its smallest member by bisection over the
+    // (ordered) bit patterns of the non-negative floats.  NaN cut -> fs_min = NaN -> nothing passes.
+    {
+        const float cutf = (float)cut;
+        uint32_t lo = 0u, hi = 0x7f800000u;           // f(+0) = 0 never passes a cut >= 0; f(inf) = inf
+        float fs_min = nb::u2f(0x7fc00000u);
+        if (cutf == cutf && sqrtf(nb::u2f(hi)) / max_abs > cutf) {
+            if (sqrtf(nb::u2f(lo)) / max_abs > cutf) hi = lo;
+            while (hi - lo > 1u) {
+                const uint32_t mid = lo + (hi - lo) / 2u;
+                if (sqrtf(nb::u2f(mid)) / max_abs > cutf) hi = mid; else lo = mid;
+            }
+            fs_min = nb::u2f(hi);
+        }
+        sp[NB200_SP_FROBSQ_MIN] = (double)fs_min;
+    }
     sp[NB200_SP_FROB_THR] = thr;
     sp[NB200_SP_FROB_CUT] = cut;
     sp[NB200_SP_SKIP] = any ? 0.0 : 1.0;

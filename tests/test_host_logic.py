@@ -100,6 +100,18 @@ def test_np_expf_is_bit_exact(hostmath):
         ref = np.exp(x)
     assert np.array_equal(y.view(np.uint32)[~np.isnan(ref)], ref.view(np.uint32)[~np.isnan(ref)])
     assert np.isnan(y[np.isnan(ref)]).all()
+    # the straight-line variant used by the vesselness (x <= 0 or NaN), incl. the gradual-underflow tail
+    neg = x[~(x > 0)]
+    y2 = np.empty_like(neg)
+    hostmath.hm_expf_nonpos(_vp(neg), _vp(y2), C.c_long(neg.size))
+    with np.errstate(all="ignore"):
+        ref2 = np.exp(neg)
+    ok = ~np.isnan(ref2)
+    assert np.array_equal(y2.view(np.uint32)[ok], ref2.view(np.uint32)[ok])
+    tail = np.linspace(-104.5, -86.0, 200001).astype(np.float32)
+    y3 = np.empty_like(tail)
+    hostmath.hm_expf_nonpos(_vp(tail), _vp(y3), C.c_long(tail.size))
+    assert np.array_equal(y3.view(np.uint32), np.exp(tail).view(np.uint32))
 
 
 def _eig_ref(h6):
