@@ -85,3 +85,18 @@ def test_filter_2d_matches_reference():
     fin = f.filter_frame_host(g["raw"])
     assert np.array_equal(fin > 0, g["frangi"] > 0)
     assert frangi_tolerance(fin, g["frangi"]).all()
+
+
+def test_z_sharded_equals_single_gpu():
+    """Needs >= 2 GPUs (skipped on the single-GPU round-end run): torchrun scripts/zshard_check.py."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "scripts", "zshard_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,0 +1,82 @@
+"""Host-side logic of the multi-GPU path, exercised on CPU with the gloo backend (world_size 2 and 3)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nz, halo, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nellie_b200.sharding import ZComm, z_partition
+        parts = z_partition(nz, world)
+        z0, z1 = parts[rank]
+        pad_lo, pad_hi = min(halo, z0), min(halo, nz - z1)
+        ny, nx = 5, 7
+        full = torch.arange(nz * ny * nx, dtype=torch.float32).reshape(nz, ny, nx)     # the "global frame"
+        buf = torch.full((pad_lo + (z1 - z0) + pad_hi, ny, nx), -1.0)
+        buf[pad_lo:pad_lo + z1 - z0] = full[z0:z1]
+        comm = ZComm(z1 - z0, pad_lo, pad_hi)
+        for depth in (1, halo):
+            buf2 = buf.clone()
+            comm.exchange_halo(buf2, depth)
+            lo = depth if rank > 0 else 0
+            hi = depth if rank < world - 1 else 0
+            want = full[z0 - lo:z1 + hi]
+            got = buf2[pad_lo - lo:pad_lo + (z1 - z0) + hi]
+            assert torch.equal(got, want), (rank, depth)
+        # threshold state: min key / max key / count / bins
+        state = torch.zeros(3 + 256, dtype=torch.int64)
+        state[0] = 1000 + 10 * rank if rank != 1 else 0xFFFFFFFF      # rank 1 has no samples
+        state[1] = 5000 + rank if rank != 1 else 0
+        state[2] = 3 * (rank + 1) if rank != 1 else 0
+        state[3:] = rank + 1 if rank != 1 else 0
+        comm.reduce_hist_minmax(state)
+        comm.reduce_hist_bins(state)
+        contributing = [r for r in range(world) if r != 1]
+        assert int(state[0]) == min(1000 + 10 * r for r in contributing)
+        assert int(state[1]) == max(5000 + r for r in contributing)
+        assert int(state[2]) == sum(3 * (r + 1) for r in contributing)
+        assert bool((state[3:] == sum(r + 1 for r in contributing)).all())
+        hs = torch.tensor([np.float32(1.5 + rank).view(np.uint32), np.float32(9.0 - rank).view(np.uint32)], dtype=torch.int64)
+        comm.reduce_hstats(hs)
+        assert int(hs[0]) == int(np.float32(1.5 + world - 1).view(np.uint32))
+        assert int(hs[1]) == int(np.float32(9.0).view(np.uint32))
+        # lattice samples: ragged lengths, zero padded
+        n = 4 + rank
+        s = torch.arange(1, n + 1, dtype=torch.float32) + 100 * rank
+        allv, total = comm.gather_samples(s, n)
+        pos = allv[:total][allv[:total] > 0]
+        want = torch.cat([torch.arange(1, 5 + r, dtype=torch.float32) + 100 * r for r in range(world)])
+        assert torch.equal(torch.sort(pos).values, torch.sort(want).values)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nz,halo", [(2, 16, 3), (3, 17, 4)])
+def test_zcomm_collectives_gloo(world, nz, halo, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), nz, halo, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_partitions():
+    from nellie_b200.sharding import frames_of_rank, z_partition
+    assert z_partition(1024, 8) == [(128 * i, 128 * (i + 1)) for i in range(8)]
+    p = z_partition(17, 3)
+    assert p == [(0, 6), (6, 12), (12, 17)] and p[-1][1] == 17
+    frames = [frames_of_rank(16, r, 4) for r in range(4)]
+    assert sorted(sum(frames, [])) == list(range(16)) and frames[1] == [1, 5, 9, 13]
