@@ -92,6 +92,12 @@ int nb200_sm_count(void);
  * axis: 0 = Z, 1 = Y, 2 = X.  src != dst. */
 int nb200_gauss_axis(const float* src, float* dst, const nb200_vol* vol, int axis,
                      const double* weights, int radius, void* stream);
+/* The Y pass followed by the X pass of the same call (axes 1 and 2 of scipy's loop, with the float32
+ * intermediate scipy stores between them) fused into one kernel: 8 B/voxel of HBM traffic for two axes
+ * instead of 16.  Same radius on both axes, 1 <= radius <= 8 (NB200_ERR_UNSUPPORTED otherwise: use two
+ * nb200_gauss_axis calls).  wy / wx: HOST double[radius+1] taps of the two axes. */
+int nb200_gauss_yx(const float* src, float* dst, const nb200_vol* vol, const double* wy, const double* wx,
+                   int radius, void* stream);
 
 /* ---- F2: threshold sampling lattice -----------------------------------------------------
  * arr[::sz, ::sy, ::sx] on the GLOBAL lattice (filtering.py:328-363); every lattice point of

@@ -46,6 +46,7 @@ _SIGS = {
     "nb200_last_error": ([], C.c_char_p),
     "nb200_sm_count": ([], C.c_int),
     "nb200_gauss_axis": ([_p, _p, C.POINTER(Vol), C.c_int, C.POINTER(C.c_double), C.c_int, _p], C.c_int),
+    "nb200_gauss_yx": ([_p, _p, C.POINTER(Vol), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, _p], C.c_int),
     "nb200_lattice_sample": ([_p, C.POINTER(Vol), C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_strided_sample": ([_p, _ll, _ll, _ll, _p, C.c_float, _p, _p], C.c_int),
     "nb200_hist_reset": ([_p, _p], C.c_int),

@@ -66,6 +66,129 @@ opening_kernel(const float* __restrict__ acc, float* __restrict__ out, nb200_vol
     }
 }
 
+// ---- Z-marching opening on bit planes (fast path: nx % 4 == 0, 16-byte aligned volumes) ----------------
+// A CTA (8 warps) owns a 128 x 36 window of the XY plane — 120 x 32 outputs plus a halo of 4 columns /
+// 2 rows — and walks along Z.  Each incoming plane is read once (one 128-bit load per lane and row) and
+// reduced to (V > thr) bits with four warp ballots per row: word k of a row holds the bit of voxel
+// 4*lane + k in bit `lane` (interleaved layout, so the x +- 1 neighbours of word k are words k +- 1, and a
+// one-bit shift of word 0 / 3 at the lane boundary).  Erosion and dilation by the 6-neighbour cross are
+// word-wide AND / OR over three-plane rings of those rows in shared memory; out-of-frame voxels count as
+// 0 (scipy border_value=0).  The output plane re-reads its accumulator values (requested two barriers
+// earlier, L2-resident) and writes V * m.  HBM traffic: 4 B read + 4 B written per voxel.
+namespace om {
+constexpr int NT = 256, NW = 8;
+constexpr int ROWS = 36, TYO = 32, TXO = 120;
+constexpr int RPW = TYO / NW;          // output rows per warp
+
+__global__ void __launch_bounds__(NT)
+opening_march_kernel(const float* __restrict__ acc, float* __restrict__ out, nb200_vol v,
+                     const double* __restrict__ thr, int zchunk) {
+    __shared__ __align__(16) unsigned m[3][ROWS][4];
+    __shared__ __align__(16) unsigned e[3][ROWS][4];
+    const bool passthrough = thr[1] == 0.0;     // no positive sample: frame returned unchanged (:959-960)
+    const float cut = (float)thr[0];
+    const int ntx = (v.nx + TXO - 1) / TXO, nty = (v.ny + TYO - 1) / TYO;
+    long long b = blockIdx.x;
+    const int bx = (int)(b % ntx); b /= ntx;
+    const int by = (int)(b % nty); b /= nty;
+    const int zs = v.zc0 + (int)b * zchunk, ze = min(zs + zchunk, v.zc1);      // buffer planes
+    if (zs >= ze) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = bx * TXO - 4 + 4 * lane;                  // first voxel of this lane's group of four
+    const int yw = by * TYO - 2;                            // y of window row 0
+    const bool x_in = x >= 0 && x < v.nx;                   // nx % 4 == 0: a group is inside or outside as a whole
+    const bool x_out = x_in && lane >= 1 && lane <= 30;
+    const long long plane = (long long)v.ny * v.nx;
+    for (int t = threadIdx.x; t < 3 * ROWS * 4; t += NT) (&e[0][0][0])[t] = 0u;
+    if (passthrough) {
+        for (int z = zs; z < ze; ++z)
+            for (int i = 0; i < RPW; ++i) {
+                const int y = yw + 2 + warp * RPW + i;
+                if (y < v.ny && x_out) {
+                    const long long at = (long long)z * plane + (long long)y * v.nx + x;
+                    const float4 a = *reinterpret_cast<const float4*>(acc + at);
+                    *reinterpret_cast<float4*>(out + at) =
+                        make_float4(fmaxf(a.x, 0.0f), fmaxf(a.y, 0.0f), fmaxf(a.z, 0.0f), fmaxf(a.w, 0.0f));
+                }
+            }
+        return;
+    }
+    // p = incoming mask plane; erosion lags one plane, the output two
+    for (int p = zs - 2; p <= ze + 1; ++p) {
+        const int zo = p - 2;                               // output plane of this step
+        const bool do_out = zo >= zs;
+        float4 cur[RPW];
+        if (do_out) {
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int y = yw + 2 + warp * RPW + i;
+                cur[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (y < v.ny && x_out)
+                    cur[i] = __ldg(reinterpret_cast<const float4*>(acc + (long long)zo * plane + (long long)y * v.nx + x));
+            }
+        }
+        // ---- phase 1: bits of plane p ----
+        {
+            const int pg = p + v.zg_off;
+            const bool z_in = pg >= 0 && pg < v.nz_glob && p >= 0 && p < v.nz_buf;
+            unsigned (*mp)[4] = m[(p + 3) % 3];
+            for (int r = warp; r < ROWS; r += NW) {
+                const int y = yw + r;
+                float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);      // 0 > cut is false for cut >= 0 ...
+                const bool ok = z_in && x_in && y >= 0 && y < v.ny;
+                if (ok) a = __ldg(reinterpret_cast<const float4*>(acc + (long long)p * plane + (long long)y * v.nx + x));
+                // ... but be explicit: out-of-frame voxels are 0 bits whatever the threshold
+                const unsigned w0 = __ballot_sync(0xffffffffu, ok && a.x > cut);
+                const unsigned w1 = __ballot_sync(0xffffffffu, ok && a.y > cut);
+                const unsigned w2 = __ballot_sync(0xffffffffu, ok && a.z > cut);
+                const unsigned w3 = __ballot_sync(0xffffffffu, ok && a.w > cut);
+                if (lane == 0) *reinterpret_cast<uint4*>(mp[r]) = make_uint4(w0, w1, w2, w3);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: erosion of plane p-1 (window rows 1..34) ----
+        if (p - 1 >= zs - 1 && threadIdx.x < 34 * 4) {
+            const int r = 1 + (threadIdx.x >> 2), k = threadIdx.x & 3;
+            const unsigned (*c)[4] = m[(p + 2) % 3];
+            const unsigned (*lo)[4] = m[(p + 1) % 3];
+            const unsigned (*hi)[4] = m[(p + 3) % 3];
+            const unsigned xm = k > 0 ? c[r][k - 1] : (c[r][3] << 1);
+            const unsigned xp = k < 3 ? c[r][k + 1] : (c[r][0] >> 1);
+            e[(p + 2) % 3][r][k] = c[r][k] & c[r - 1][k] & c[r + 1][k] & lo[r][k] & hi[r][k] & xm & xp;
+        }
+        __syncthreads();
+        // ---- phase 3: dilation + output of plane p-2 ----
+        if (do_out) {
+            const unsigned (*c)[4] = e[(p + 1) % 3];
+            const unsigned (*lo)[4] = e[(p + 0) % 3];
+            const unsigned (*hi)[4] = e[(p + 2) % 3];
+#pragma unroll
+            for (int i = 0; i < RPW; ++i) {
+                const int r = 2 + warp * RPW + i, y = yw + r;
+                const uint4 cc = *reinterpret_cast<const uint4*>(c[r]);
+                const uint4 up = *reinterpret_cast<const uint4*>(c[r - 1]);
+                const uint4 dn = *reinterpret_cast<const uint4*>(c[r + 1]);
+                const uint4 l = *reinterpret_cast<const uint4*>(lo[r]);
+                const uint4 h = *reinterpret_cast<const uint4*>(hi[r]);
+                const unsigned d0 = cc.x | up.x | dn.x | l.x | h.x | (cc.w << 1) | cc.y;
+                const unsigned d1 = cc.y | up.y | dn.y | l.y | h.y | cc.x | cc.z;
+                const unsigned d2 = cc.z | up.z | dn.z | l.z | h.z | cc.y | cc.w;
+                const unsigned d3 = cc.w | up.w | dn.w | l.w | h.w | cc.z | (cc.x >> 1);
+                if (y < v.ny && x_out) {
+                    const float4 a = cur[i];
+                    float4 o;
+                    o.x = (d0 >> lane & 1u) ? fmaxf(a.x, 0.0f) : 0.0f;
+                    o.y = (d1 >> lane & 1u) ? fmaxf(a.y, 0.0f) : 0.0f;
+                    o.z = (d2 >> lane & 1u) ? fmaxf(a.z, 0.0f) : 0.0f;
+                    o.w = (d3 >> lane & 1u) ? fmaxf(a.w, 0.0f) : 0.0f;
+                    *reinterpret_cast<float4*>(out + (long long)zo * plane + (long long)y * v.nx + x) = o;
+                }
+            }
+        }
+    }
+}
+}  // namespace om
+
 __global__ void __launch_bounds__(256)
 opening_2d_kernel(const float* __restrict__ vin, float* __restrict__ out, int ny, int nx,
                   const double* __restrict__ thr) {
@@ -104,6 +227,15 @@ int nb200_finalize_opening(const float* acc, float* out, const nb200_vol* vol, c
         const int need_lo = g0 - 2 < 0 ? 0 : g0 - 2, need_hi = g1 + 1 >= v.nz_glob ? v.nz_glob - 1 : g1 + 1;
         NB_REQUIRE(need_lo - v.zg_off >= 0 && need_hi - v.zg_off < v.nz_buf, NB200_ERR_ARG,
                    "nb200_finalize_opening: Z halo of 2 planes missing");
+    }
+    if (v.nx % 4 == 0 && (((uintptr_t)acc | (uintptr_t)out) & 15) == 0) {
+        const long long tiles = (long long)((v.nx + om::TXO - 1) / om::TXO) * ((v.ny + om::TYO - 1) / om::TYO);
+        const int nzc = v.zc1 - v.zc0;
+        int zchunk = 128;                       // 4 extra planes per chunk: two full waves of CTAs before going shorter
+        while (zchunk > 16 && tiles * ((nzc + zchunk - 1) / zchunk) < 2LL * 8 * nb::sm_count()) zchunk /= 2;
+        const long long grid = tiles * ((nzc + zchunk - 1) / zchunk);
+        om::opening_march_kernel<<<(unsigned)grid, om::NT, 0, nb::as_stream(stream)>>>(acc, out, v, thr, zchunk);
+        return nb::check_launch("finalize_opening(march)");
     }
     const long long nbx = (v.nx + TX - 1) / TX, nby = (v.ny + TY - 1) / TY, nbz = (v.zc1 - v.zc0 + TZ - 1) / TZ;
     opening_kernel<<<(unsigned)(nbx * nby * nbz), NTHREADS, 0, nb::as_stream(stream)>>>(acc, out, v, thr);

@@ -182,6 +182,7 @@ class FrangiEngine3D:
         self.fd = params.fd_spacing_f32()
         self._fd_c = self.fd.ctypes.data_as(C.POINTER(C.c_float))
         self.div_mode = self._pick_div_mode()
+        self.fuse_yx = True   # Y and X blur passes in one kernel (nb200_gauss_yx); False = one kernel per axis
         self.launches = 0
         self.profile = None   # set to a list to record (name, start, end) CUDA events per C-ABI call
         # hooks for the multi-GPU driver (identity on one GPU)
@@ -264,16 +265,23 @@ class FrangiEngine3D:
             if any(t is not None for t in taps):
                 rz = taps[0][1] if taps[0] is not None else 0
                 self.exchange_halo(self.gauss[self.cur], rz + 2)
+                # Z pass over owned+2 planes (reads the exchanged halo); Y/X passes likewise so the
+                # Hessian stencil finds blurred neighbours without a second exchange
+                v = self.vol(2, 2)
+                dp = C.POINTER(C.c_double)
+                fuse_yx = (self.fuse_yx and taps[1] is not None and taps[2] is not None
+                           and taps[1][1] == taps[2][1] and 1 <= taps[1][1] <= 8)
                 for axis, t in enumerate(taps):
                     if t is None or t[1] == 0:
                         continue
                     w, r = t
                     src, dst = self.gauss[self.cur], self.gauss[1 - self.cur]
-                    # Z pass over owned+2 planes (reads the exchanged halo); Y/X passes likewise so the
-                    # Hessian stencil finds blurred neighbours without a second exchange
-                    v = self.vol(2, 2)
-                    self._call("nb200_gauss_axis", _ptr(src), _ptr(dst), C.byref(v), axis,
-                               w.ctypes.data_as(C.POINTER(C.c_double)), r, st)
+                    if axis == 1 and fuse_yx:
+                        self._call("nb200_gauss_yx", _ptr(src), _ptr(dst), C.byref(v), w.ctypes.data_as(dp),
+                                   taps[2][0].ctypes.data_as(dp), r, st)
+                        self.cur = 1 - self.cur
+                        break
+                    self._call("nb200_gauss_axis", _ptr(src), _ptr(dst), C.byref(v), axis, w.ctypes.data_as(dp), r, st)
                     self.cur = 1 - self.cur
             g = self.gauss[self.cur]
             own = self.vol()
@@ -300,8 +308,9 @@ class FrangiEngine3D:
             self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode,
                        float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
 
-    def finalize(self, apply_mask_volume=True):
-        """filtering.py:926 (V*masks) + :1014-1018 / :952-967 (_mask_volume)."""
+    def finalize(self, apply_mask_volume=True, out=None):
+        """filtering.py:926 (V*masks) + :1014-1018 / :952-967 (_mask_volume).  ``out``: optional device buffer of
+        the owned-planes shape that receives the frame instead of the engine's own ``self.out``."""
         st = _stream()
         own = self.vol()
         sz, sy, sx = self.strides
@@ -313,23 +322,25 @@ class FrangiEngine3D:
             self.pct.zero_()   # pct[1] == 0 -> pass-through
         self.exchange_halo(self.acc, 2)
         # output is written for the owned planes only; give the kernel a view whose plane 0 is buffer plane 0
-        out_full = self.out if self.nz_buf == self.nz_own else None
-        if out_full is None:
+        dst = self.out if out is None else out
+        if tuple(dst.shape) != tuple(self.out.shape) or dst.dtype != torch.float32 or not dst.is_contiguous():
+            raise ValueError("finalize: out must be a contiguous float32 tensor of the owned-planes shape")
+        if self.nz_buf != self.nz_own:
             if not hasattr(self, "_out_buf"):
                 self._out_buf = torch.empty_like(self.acc)
             self._call("nb200_finalize_opening", _ptr(self.acc), _ptr(self._out_buf), C.byref(own), _ptr(self.pct), st)
-            self.out.copy_(self._out_buf[self.pad_lo:self.pad_lo + self.nz_own])
+            dst.copy_(self._out_buf[self.pad_lo:self.pad_lo + self.nz_own])
         else:
-            self._call("nb200_finalize_opening", _ptr(self.acc), _ptr(self.out), C.byref(own), _ptr(self.pct), st)
-        return self.out
+            self._call("nb200_finalize_opening", _ptr(self.acc), _ptr(dst), C.byref(own), _ptr(self.pct), st)
+        return dst
 
-    def filter_frame(self, frame: torch.Tensor, apply_mask_volume=True) -> torch.Tensor:
-        """Device tensor in, device tensor out (the engine's own output buffer)."""
+    def filter_frame(self, frame: torch.Tensor, apply_mask_volume=True, out=None) -> torch.Tensor:
+        """Device tensor in, device tensor out (the engine's own output buffer unless ``out`` is given)."""
         if self.p.remove_edges:
             raise NotImplementedError("remove_edges (filtering.py:969-1000) is not implemented on the B200 path yet")
         self.load_frame(frame)
         self.run_sigmas()
-        return self.finalize(apply_mask_volume)
+        return self.finalize(apply_mask_volume, out=out)
 
     def mask_volume(self, v: torch.Tensor) -> torch.Tensor:
         """_mask_volume (filtering.py:952-967) of an already computed response ``v`` (>= 0)."""

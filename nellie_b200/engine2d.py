@@ -98,7 +98,14 @@ class FrangiEngine2D:
         self._call("nb200_hist_minmax", _ptr(self.samples), n, transform, divisor_ptr, _ptr(self.hist), st)
         self._call("nb200_hist_bins", _ptr(self.samples), n, transform, divisor_ptr, _ptr(self.hist), st)
 
-    def filter_frame(self, frame: torch.Tensor, apply_mask_volume=True) -> torch.Tensor:
+    def filter_frame(self, frame: torch.Tensor, apply_mask_volume=True, out=None) -> torch.Tensor:
+        res = self._filter_frame(frame, apply_mask_volume)
+        if out is None:
+            return res
+        out.copy_(res)
+        return out
+
+    def _filter_frame(self, frame: torch.Tensor, apply_mask_volume=True) -> torch.Tensor:
         if self.p.remove_edges:
             raise NotImplementedError("remove_edges (filtering.py:969-1000) is not implemented on the B200 path yet")
         st = _stream()

@@ -194,18 +194,34 @@ class Filter:
 
     # ---- top level (reference: filtering.py:1005-1076) -------------------------------------------
     def _run_filter(self, mask=True):
-        for t in range(self.num_t):
+        """T loop of filtering.py:1005-1031 as a pipelined frame stream (pipeline.py): the upload of frame
+        t+1 and the download + memmap write of frame t-1 overlap the kernels of frame t."""
+        if not mask:
+            raise NotImplementedError("mask=False is not implemented on the B200 path")
+        from .pipeline import FramePipeline
+        single = bool(self.im_info.no_t) or self.num_t == 1
+        frame_shape = tuple(self.im_memmap.shape[1:])          # the reference indexes im_memmap[t, ...] (T always present)
+        eng = self._engine_for(frame_shape)
+
+        def get_in(t):
+            return self.im_memmap[t, ...]
+
+        def get_out(t):
+            if self.frangi_memmap.ndim == len(frame_shape):
+                return self.frangi_memmap
+            return self.frangi_memmap[0 if single else t]
+
+        def on_frame(t):
             if self.viewer is not None:
                 self.viewer.status = f"Preprocessing. Frame: {t + 1} of {self.num_t}."
-            if not mask:
-                raise NotImplementedError("mask=False is not implemented on the B200 path")
-            filtered = self.filter_frame_host(self.im_memmap[t, ...])
-            if self.im_info.no_t or self.num_t == 1:
-                self.frangi_memmap[:] = filtered[:]
-            else:
-                self.frangi_memmap[t, ...] = filtered
+
+        def after_store(t):
             if hasattr(self.frangi_memmap, "flush"):
                 self.frangi_memmap.flush()
+
+        with torch.cuda.device(eng.device):
+            FramePipeline(eng).run(self.num_t, get_in, get_out, apply_mask_volume=True, on_frame=on_frame,
+                                   after_store=after_store)
 
     def run(self, mask=True):
         logger.info("Running Frangi filter (nellie_b200).")

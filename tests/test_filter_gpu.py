@@ -100,3 +100,68 @@ def test_z_sharded_equals_single_gpu():
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
                         os.path.join(root, "scripts", "zshard_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+class _MemInfo:
+    """Duck-typed im_info (tests/test_labelling.py:16-22 of the reference) with in-memory 'memmaps'."""
+
+    def __init__(self, raw_t, dim_res, no_z=False):
+        self.no_t, self.no_z = False, no_z
+        self.shape = raw_t.shape
+        self.axes = "TYX" if no_z else "TZYX"
+        self.dim_res = dim_res
+        self.im_path = "raw"
+        self.pipeline_paths = {"im_preprocessed": "pre"}
+        self._raw = raw_t
+        self.allocated = {}
+
+    def get_memmap(self, path):
+        return self._raw
+
+    def allocate_memory(self, path, dtype="float32", description="", return_memmap=True):
+        self.allocated[path] = np.zeros(self.shape, dtype=dtype)
+        return self.allocated[path]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.uint16])
+def test_run_streams_frames_through_the_pipeline(dtype):
+    """Filter.run() (filtering.py:1033-1076): T loop as the double-buffered H2D/compute/D2H stream; every
+    frame must equal the one-frame-at-a-time result, inputs untouched, output written per frame."""
+    from nellie_b200 import Filter
+    from nellie_b200.phantoms import tubular_phantom_np
+    dim_res = {"X": 0.1, "Y": 0.1, "Z": 0.2, "T": 1.0}
+    frames = np.stack([tubular_phantom_np((20, 48, 64), seed=300 + t, n_tubes=5) for t in range(5)])
+    frames = np.clip(frames, 0, 60000).astype(dtype)
+    before = frames.copy()
+    info = _MemInfo(frames, dim_res)
+    f = Filter(info, device="b200")
+    f.run()
+    out = info.allocated["pre"]
+    assert np.array_equal(frames, before)
+    g = Filter(info, device="b200")
+    g._get_t()
+    g._set_default_sigmas()
+    for t in range(frames.shape[0]):
+        want = g.filter_frame_host(frames[t])
+        assert np.array_equal(out[t], want), t
+        assert (want > 0).any()
+
+
+def test_pipeline_with_pinned_buffers():
+    """The zero-staging mode bench.py's e2e uses: pinned tensors in and out, copies on side streams."""
+    import torch
+    from nellie_b200.engine import FilterParams, FrangiEngine3D
+    from nellie_b200.phantoms import tubular_phantom_np
+    from nellie_b200.pipeline import FramePipeline
+    dim_res = {"X": 0.1, "Y": 0.1, "Z": 0.1, "T": 1.0}
+    shape = (24, 40, 64)
+    eng = FrangiEngine3D(shape, FilterParams(dim_res=dim_res), device="cuda")
+    ins = [torch.from_numpy(tubular_phantom_np(shape, seed=40 + t, n_tubes=4)).pin_memory() for t in range(4)]
+    outs = [torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(4)]
+    pipe = FramePipeline(eng)
+    pipe.run(4, lambda t: ins[t], lambda t: outs[t])
+    torch.cuda.synchronize()
+    assert pipe.h2d_bytes == 4 * ins[0].numel() * 4 and pipe.d2h_bytes == pipe.h2d_bytes
+    for t in range(4):
+        want = eng.filter_frame(ins[t].cuda()).cpu()
+        assert torch.equal(outs[t], want), t

@@ -87,3 +87,75 @@ def test_divisor_modes():
     for d, want in [(0.25, 2), (0.5, 2), (1.0, 2), (0.1, 1), (0.2, 1), (0.4, 1), (0.0655, 1), (0.131, 1)]:
         _cabi.check(lib.nb200_divisor_mode(C.c_float(np.float32(d)), C.byref(m), st), "nb200_divisor_mode")
         assert m.value == want, (d, m.value)
+
+
+# scipy.ndimage.gaussian_filter is the third-party primitive the reference calls (filtering.py:828-835);
+# the vectorised Z march and the fused Y+X tile kernel must reproduce it bit for bit at every radius,
+# for shapes that are not multiples of the tile and for lines shorter than the radius (repeated reflection).
+@pytest.mark.parametrize("shape", [(37, 70, 132), (9, 33, 248), (5, 3, 12), (40, 130, 131)])
+@pytest.mark.parametrize("sigma", [0.3, 0.6, 0.98, 1.3, 1.7, 2.0, 2.3, 2.7])
+def test_gauss_z_vec_and_fused_yx_match_scipy(shape, sigma):
+    import scipy.ndimage as ndi
+    import torch
+    from nellie_b200 import _cabi
+    from nellie_b200._cabi import Vol
+    from nellie_b200.engine import gaussian_taps
+    rng = np.random.default_rng(int(sigma * 100) + shape[2])
+    x = (rng.random(shape, dtype=np.float32) * 500.0).astype(np.float32)
+    w, r = gaussian_taps(sigma, 3.0)
+    assert 1 <= r <= 8
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    dp = C.POINTER(C.c_double)
+    v = Vol.whole(*shape)
+    a = torch.from_numpy(x).cuda()
+    b = torch.empty_like(a)
+    c = torch.empty_like(a)
+    _cabi.call("nb200_gauss_axis", _vp(a), _vp(b), C.byref(v), 0, w.ctypes.data_as(dp), r, st)
+    ref_z = ndi.gaussian_filter1d(x, sigma, axis=0, truncate=3.0, mode="reflect")
+    assert np.array_equal(b.cpu().numpy(), ref_z)
+    _cabi.call("nb200_gauss_yx", _vp(b), _vp(c), C.byref(v), w.ctypes.data_as(dp), w.ctypes.data_as(dp), r, st)
+    ref = ndi.gaussian_filter(x, sigma, truncate=3.0, mode="reflect")
+    assert np.array_equal(c.cpu().numpy(), ref)
+    # and the per-axis kernels agree with the fused one
+    d = torch.empty_like(a)
+    _cabi.call("nb200_gauss_axis", _vp(b), _vp(d), C.byref(v), 1, w.ctypes.data_as(dp), r, st)
+    _cabi.call("nb200_gauss_axis", _vp(d), _vp(b), C.byref(v), 2, w.ctypes.data_as(dp), r, st)
+    assert torch.equal(b, c)
+
+
+# _mask_volume's opening (filtering.py:964-966) on the marching bit-plane kernel (nx % 4 == 0) and on the
+# brick fallback (any nx), against scipy.ndimage.binary_opening itself; also as a Z window of a taller buffer.
+@pytest.mark.parametrize("shape", [(70, 75, 256), (5, 9, 12), (33, 40, 131), (140, 33, 124)])
+@pytest.mark.parametrize("density", [0.5, 0.85])
+def test_opening_matches_scipy(shape, density):
+    import scipy.ndimage as ndi
+    import torch
+    from nellie_b200 import _cabi
+    from nellie_b200._cabi import Vol
+    rng = np.random.default_rng(shape[2])
+    vol = rng.random(shape, dtype=np.float32)
+    vol = ndi.uniform_filter(vol, 3).astype(np.float32)          # blobs, so that the opening keeps something
+    cut = float(np.quantile(vol, 1.0 - density))
+    vol[rng.random(shape) < 0.05] = -1.0                          # dead voxels of the accumulator
+    v_pos = np.maximum(vol, 0.0)
+    ref = v_pos * ndi.binary_opening(v_pos > np.float32(cut))
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    acc = torch.from_numpy(vol).cuda()
+    out = torch.full_like(acc, 7.0)
+    thr = torch.tensor([np.float32(cut), 1.0], dtype=torch.float64, device="cuda")
+    v = Vol.whole(*shape)
+    _cabi.call("nb200_finalize_opening", _vp(acc), _vp(out), C.byref(v), _vp(thr), st)
+    assert np.array_equal(out.cpu().numpy(), ref)
+    assert ref.any()
+    # pass-through when there is no positive sample
+    thr0 = torch.tensor([0.0, 0.0], dtype=torch.float64, device="cuda")
+    _cabi.call("nb200_finalize_opening", _vp(acc), _vp(out), C.byref(v), _vp(thr0), st)
+    assert np.array_equal(out.cpu().numpy(), v_pos)
+    # slab window: planes [3, nz-2) of the same buffer must equal the same planes of the whole-frame result
+    if shape[0] > 8:
+        out2 = torch.full_like(acc, 7.0)
+        w = Vol(shape[0], shape[1], shape[2], 3, shape[0] - 2, 0, shape[0])
+        _cabi.call("nb200_finalize_opening", _vp(acc), _vp(out2), C.byref(w), _vp(thr), st)
+        got = out2.cpu().numpy()
+        assert np.array_equal(got[3:shape[0] - 2], ref[3:shape[0] - 2])
+        assert (got[:3] == 7.0).all() and (got[shape[0] - 2:] == 7.0).all()
