@@ -141,6 +141,13 @@ int nb200_finalize_label_threshold(const long long* state, int log_domain, doubl
 int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
                         const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
                         void* stream);
+/* Same, and additionally leaves one float per voxel in `code` (volume of the buffer shape, planes [zc0,zc1)
+ * written) for nb200_frangi_sparse: |code| = frob_sq as the mask tests it, sign bit set when the vesselness of
+ * the voxel is provably zero (a pair of diagonal Hessian entries with a clearly positive sum: lambda_2 or
+ * lambda_3 > 0, filtering.py:759-761).  code may be NULL (plain nb200_hessian_stats). */
+int nb200_hessian_stats_code(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
+                             const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
+                             float* code, void* stream);
 /* Division mode for one grid-spacing divisor d = fl32(h) or fl32(2h) (synchronous, init time only):
  *   2 (NB200_DIV_POW2)  d is a power of two: multiply by the exact reciprocal;
  *   1 (NB200_DIV_FAST)  q = fma(fma(-n*r, d, n), r, n*r), r = RN(1/d), verified HERE bit-for-bit against IEEE
@@ -163,6 +170,12 @@ int nb200_hessian_components(const float* gauss, const nb200_vol* vol, const flo
  * first sigma.  Reads gamma_sq / frob cut / max_abs / skip from the device record `sp`. */
 int nb200_frangi_accumulate(const float* gauss, float* acc, const nb200_vol* vol, const float* spacing,
                             int div_mode, float alpha_sq, float beta_sq, const double* sp, void* stream);
+/* The same step from the record of nb200_hessian_stats_code: the dense part only streams code and acc
+ * (12 B/voxel); Hessian, eigenvalues and vesselness are evaluated for the few percent of voxels that are
+ * alive, pass the mask and are not provably zero, compacted through shared-memory work queues.  Results are
+ * bit-identical to nb200_frangi_accumulate. */
+int nb200_frangi_sparse(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
+                        const float* spacing, float alpha_sq, float beta_sq, const double* sp, void* stream);
 /* 2-D variant (closed-form 2x2 eigenvalues, filtering.py:676-690, :737-741); spacing[4] = y,x */
 int nb200_frangi_accumulate_2d(const float* gauss, float* acc, int ny, int nx, const float* spacing,
                                float beta_sq, const double* sp, void* stream);

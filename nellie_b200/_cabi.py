@@ -58,6 +58,9 @@ _SIGS = {
     "nb200_finalize_label_threshold": ([_p, C.c_int, _p, _p], C.c_int),
     "nb200_hessian_stats": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p],
                             C.c_int),
+    "nb200_hessian_stats_code": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p,
+                                  _p, _p], C.c_int),
+    "nb200_frangi_sparse": ([_p, _p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_float, C.c_float, _p, _p], C.c_int),
     "nb200_hessian_components": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, _p], C.c_int),
     "nb200_divisor_mode": ([C.c_float, C.POINTER(C.c_int), _p], C.c_int),
     "nb200_hstats_reset": ([_p, _p], C.c_int),

@@ -86,7 +86,22 @@ struct StatsParams {
     int sz, sy, sx, g_first, ly_n, lx_n;
     float* frob_samples;
     long long* hstats;
+    float* code;            // optional per-voxel record for nb200_frangi_sparse (see voxel_code)
+    int code_vec_ok;
 };
+
+// Per-voxel record K2 leaves for the sparse K3:  |code| = frob_sq (exactly the value the mask tests), sign bit
+// set when the vesselness is PROVABLY zero.  The proof is the diagonal test of devmath.cuh (pd_reject_diag) with
+// the margin taken relative to the voxel's own Frobenius norm instead of the sigma-wide bound: a pair of diagonal
+// entries with a_ii + a_jj > 1e-5 * F, F >= ||H||_F, forces lambda_2 > 0 or lambda_3 > 0 far beyond any
+// rounding of the eigenvalues, so filtering.py:759-761 zeroes the response.  ||H||_F^2 is frob_sq itself; the
+// comparison is done on squares (m > 0, m^2 > 1.001e-10 * frob_sq; the 1e-3 slack dwarfs the float32 rounding
+// of frob_sq and m^2) and only for norms in the range pd_margins accepts, where nothing under- or overflows.
+__device__ __forceinline__ float voxel_code(float fs, float zz, float yy, float xx) {
+    const float m = fmaxf(fmaxf(zz + yy, zz + xx), yy + xx);
+    const bool zero = m > 0.0f && m * m > 1.001e-10f * fs && fs > 1e-20f && fs < 1e20f;
+    return zero ? __uint_as_float(__float_as_uint(fs) | 0x80000000u) : fs;
+}
 
 struct StatsEpi {
     const StatsParams& p;
@@ -116,12 +131,18 @@ struct StatsEpi {
     }
     __device__ __forceinline__ void prefetch(int, bool, long long) {}
     __device__ __forceinline__ void cta_sync_point() {}
-    __device__ __forceinline__ void voxels4(int row, bool valid, long long, const Hess4& h) {
+    __device__ __forceinline__ void voxels4(int row, bool valid, long long idx, const Hess4& h) {
         if (!valid) return;
         const float4 fs = frob_sq4(h);
         m_abs = fmaxf(m_abs, fmaxf(fmaxf(fmaxf(absmax4(h.zz), absmax4(h.zy)), fmaxf(absmax4(h.zx), absmax4(h.yy))),
                                    fmaxf(absmax4(h.yx), absmax4(h.xx))));
         m_frob = fmaxf(m_frob, fmaxf(fmaxf(fs.x, fs.y), fmaxf(fs.z, fs.w)));
+        if (p.code) {
+            const float4 c = make_float4(voxel_code(fs.x, h.zz.x, h.yy.x, h.xx.x), voxel_code(fs.y, h.zz.y, h.yy.y, h.xx.y),
+                                         voxel_code(fs.z, h.zz.z, h.yy.z, h.xx.z), voxel_code(fs.w, h.zz.w, h.yy.w, h.xx.w));
+            if (p.code_vec_ok) *reinterpret_cast<float4*>(p.code + idx) = c;
+            else { p.code[idx] = c.x; p.code[idx + 1] = c.y; p.code[idx + 2] = c.z; p.code[idx + 3] = c.w; }
+        }
         if (zrow >= 0 && ylat[row] >= 0) {            // lattice row: a few threads per plane
             const float* f = &fs.x;
             long long idx = (zrow + ylat[row]) * p.lx_n + xlat;
@@ -502,6 +523,7 @@ shell_stats_kernel(const float* __restrict__ g, Shell sh, nb::Spacing3 sp, Stats
         m_abs = fmaxf(m_abs, fmaxf(fmaxf(fmaxf(fabsf(h.zz), fabsf(h.zy)), fmaxf(fabsf(h.zx), fabsf(h.yy))),
                                    fmaxf(fabsf(h.yx), fabsf(h.xx))));
         m_frob = fmaxf(m_frob, fs);
+        if (p.code) p.code[idx] = voxel_code(fs, h.zz, h.yy, h.xx);
         const int zg = zb + sh.v.zg_off;
         if (p.frob_samples && zg % p.sz == 0 && y % p.sy == 0 && x % p.sx == 0)
             p.frob_samples[((long long)((zg - p.g_first) / p.sz) * p.ly_n + y / p.sy) * p.lx_n + x / p.sx] = sqrtf(fs);
@@ -823,8 +845,15 @@ int nb200_divisor_mode(float d, int* mode_out, void* stream) {
 
 int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode, const double* sp,
                         int sz, int sy, int sx, float* frob_samples, long long* hstats, void* stream) {
+    return nb200_hessian_stats_code(gauss, vol, spacing, div_mode, sp, sz, sy, sx, frob_samples, hstats, nullptr, stream);
+}
+
+int nb200_hessian_stats_code(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
+                             const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
+                             float* code, void* stream) {
     NB_REQUIRE(gauss && vol && spacing && hstats && sz > 0 && sy > 0 && sx > 0, NB200_ERR_ARG,
                "nb200_hessian_stats: bad argument");
+    NB_REQUIRE(code != gauss, NB200_ERR_ARG, "nb200_hessian_stats: code must not alias the blurred volume");
     NB_REQUIRE(div_mode >= 0 && div_mode <= 2, NB200_ERR_ARG, "nb200_hessian_stats: div_mode %d", div_mode);
     const nb200_vol v = *vol;
     int rc = check_vol(v, "nb200_hessian_stats");
@@ -838,6 +867,8 @@ int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* s
     p.lx_n = (v.nx + sx - 1) / sx;
     p.frob_samples = frob_samples;
     p.hstats = hstats;
+    p.code = code;
+    p.code_vec_ok = (v.nx % 4 == 0) && ((reinterpret_cast<unsigned long long>(code) & 15ull) == 0);
     cudaStream_t st = nb::as_stream(stream);
     rc = launch_march<StatsEpi>(gauss, v, spacing, div_mode, sp, 0, p, st, "hessian_stats");
     if (rc) return rc;

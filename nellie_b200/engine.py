@@ -182,6 +182,7 @@ class FrangiEngine3D:
         self.fd = params.fd_spacing_f32()
         self._fd_c = self.fd.ctypes.data_as(C.POINTER(C.c_float))
         self.div_mode = self._pick_div_mode()
+        self.sparse_k3 = True  # K3 from K2's per-voxel record (nb200_frangi_sparse); False = dense march (nb200_frangi_accumulate)
         self.fuse_yx = True   # Y and X blur passes in one kernel (nb200_gauss_yx); False = one kernel per axis
         self.launches = 0
         self.profile = None   # set to a list to record (name, start, end) CUDA events per C-ABI call
@@ -291,8 +292,10 @@ class FrangiEngine3D:
             self._call("nb200_finalize_gamma", _ptr(self.hist), _ptr(sp_i), st)
             # F4: Hessian statistics (max|H|, max frob^2, frob samples)
             self._call("nb200_hstats_reset", _ptr(self.hstats), st)
-            self._call("nb200_hessian_stats", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
-                       sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), st)
+            # the other ping-pong volume is free between two blurs: K2 leaves its per-voxel record there
+            code = self.gauss[1 - self.cur] if self.sparse_k3 else None
+            self._call("nb200_hessian_stats_code", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
+                       sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), _ptr(code), st)
             self.reduce_hstats(self.hstats)
             self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
             # F5: Frobenius threshold
@@ -305,8 +308,12 @@ class FrangiEngine3D:
                 self._call("nb200_hist_reset", _ptr(self.hist), st)
             self._call("nb200_finalize_frob", _ptr(self.hist), _ptr(self.hstats), fixed, division, _ptr(sp_i), st)
             # F4-F9 fused
-            self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode,
-                       float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
+            if self.sparse_k3:
+                self._call("nb200_frangi_sparse", _ptr(g), _ptr(code), _ptr(self.acc), C.byref(own), self._fd_c,
+                           float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
+            else:
+                self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode,
+                           float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
 
     def finalize(self, apply_mask_volume=True, out=None):
         """filtering.py:926 (V*masks) + :1014-1018 / :952-967 (_mask_volume).  ``out``: optional device buffer of
