@@ -78,7 +78,10 @@ typedef struct nb200_vol {
 /* int64[NB200_HS_WORDS] device record reduced by nb200_hessian_stats */
 #define NB200_HS_MAX_ABS_BITS 0   /* float bits of max|H| */
 #define NB200_HS_MAX_FROBSQ_BITS 1 /* float bits of max frob_sq */
-#define NB200_HS_WORDS 2
+#define NB200_HS_MIN_NZ_COMPL 2   /* 0x7f800000 - float bits of the smallest non-zero |blurred value| (0 = none seen);
+                                     complemented so that every word of the record reduces with MAX */
+#define NB200_HS_MAX_G_BITS 3     /* float bits of the largest |blurred value| */
+#define NB200_HS_WORDS 4
 
 int nb200_abi_version(void);
 const char* nb200_last_error(void);
@@ -148,6 +151,15 @@ int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* s
 int nb200_hessian_stats_code(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
                              const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
                              float* code, void* stream);
+/* Safety net of the fast constant-divisor division (NB200_DIV_FAST): nb200_hessian_stats[_code] also reduces the
+ * range of the non-zero blurred values; nb200_finalize_max_abs sets sp[NB200_SP_UNSAFE] when that range could
+ * produce a numerator outside the exponents the division was verified on.  This call then recomputes the
+ * statistics (and code) with IEEE division — it enqueues kernels that return immediately when the flag is clear,
+ * and is a no-op for the other division modes.  Call it after nb200_finalize_max_abs, then reduce hstats and
+ * finalize again. */
+int nb200_hessian_stats_redo(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
+                             const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
+                             float* code, void* stream);
 /* Division mode for one grid-spacing divisor d = fl32(h) or fl32(2h) (synchronous, init time only):
  *   2 (NB200_DIV_POW2)  d is a power of two: multiply by the exact reciprocal;
  *   1 (NB200_DIV_FAST)  q = fma(fma(-n*r, d, n), r, n*r), r = RN(1/d), verified HERE bit-for-bit against IEEE
@@ -175,7 +187,8 @@ int nb200_frangi_accumulate(const float* gauss, float* acc, const nb200_vol* vol
  * alive, pass the mask and are not provably zero, compacted through shared-memory work queues.  Results are
  * bit-identical to nb200_frangi_accumulate. */
 int nb200_frangi_sparse(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
-                        const float* spacing, float alpha_sq, float beta_sq, const double* sp, void* stream);
+                        const float* spacing, int div_mode, float alpha_sq, float beta_sq, const double* sp,
+                        void* stream);
 /* 2-D variant (closed-form 2x2 eigenvalues, filtering.py:676-690, :737-741); spacing[4] = y,x */
 int nb200_frangi_accumulate_2d(const float* gauss, float* acc, int ny, int nx, const float* spacing,
                                float beta_sq, const double* sp, void* stream);

@@ -12,7 +12,7 @@ from . import build as _build
 
 HIST_WORDS = 3 + 256
 SP_WORDS = 12
-HS_WORDS = 2
+HS_WORDS = 4
 SP_GAMMA, SP_GAMMA_SQ, SP_FROB_THR, SP_FROB_CUT, SP_MAX_ABS, SP_SKIP, SP_STATUS, SP_TRI, SP_OTSU, SP_UNSAFE = range(10)
 DIV_IEEE, DIV_FAST, DIV_POW2 = 0, 1, 2
 TF_NONE, TF_DIV, TF_LOG10 = 0, 1, 2
@@ -60,7 +60,9 @@ _SIGS = {
                             C.c_int),
     "nb200_hessian_stats_code": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p,
                                   _p, _p], C.c_int),
-    "nb200_frangi_sparse": ([_p, _p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_float, C.c_float, _p, _p], C.c_int),
+    "nb200_hessian_stats_redo": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p,
+                                  _p, _p], C.c_int),
+    "nb200_frangi_sparse": ([_p, _p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, _p, _p], C.c_int),
     "nb200_hessian_components": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, _p], C.c_int),
     "nb200_divisor_mode": ([C.c_float, C.POINTER(C.c_int), _p], C.c_int),
     "nb200_hstats_reset": ([_p, _p], C.c_int),

@@ -103,9 +103,18 @@ __device__ __forceinline__ float voxel_code(float fs, float zz, float yy, float 
     return zero ? __uint_as_float(__float_as_uint(fs) | 0x80000000u) : fs;
 }
 
+// range record of the blurred values (see NB200_HS_MIN_NZ_COMPL): NaN / inf count as "out of range"
+__device__ __forceinline__ void store_range(long long* hstats, float g_min, float g_max) {
+    if (g_min < INFINITY)
+        atomicMax((unsigned long long*)&hstats[NB200_HS_MIN_NZ_COMPL], (unsigned long long)(0x7f800000u - nb::f2u(g_min)));
+    if (!(g_max <= 3.0e38f)) g_max = INFINITY;     // NaN propagates as "unsafe"
+    atomicMax((unsigned long long*)&hstats[NB200_HS_MAX_G_BITS], (unsigned long long)nb::f2u(g_max));
+}
+
 struct StatsEpi {
     const StatsParams& p;
     float m_abs = 0.0f, m_frob = 0.0f;
+    float g_min = INFINITY, g_max = 0.0f;   // smallest non-zero and largest |blurred value| seen by this thread
     int xmask = 0, xlat = 0;            // lattice columns inside this thread's 4-voxel group (loop invariant)
     int ylat[2];                        // lattice row index of each output row, or -1
     long long zrow = -1;                // lattice plane offset of the current plane, or -1 (uniform)
@@ -131,6 +140,15 @@ struct StatsEpi {
     }
     __device__ __forceinline__ void prefetch(int, bool, long long) {}
     __device__ __forceinline__ void cta_sync_point() {}
+    // range of the non-zero blurred values (zero-filled out-of-frame parts of a tile do not count)
+    __device__ __forceinline__ void center(const float4& a, const float4& b) {
+        const float v[8] = {fabsf(a.x), fabsf(a.y), fabsf(a.z), fabsf(a.w), fabsf(b.x), fabsf(b.y), fabsf(b.z), fabsf(b.w)};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            g_max = fmaxf(g_max, v[k]);
+            g_min = fminf(g_min, v[k] > 0.0f ? v[k] : INFINITY);
+        }
+    }
     __device__ __forceinline__ void voxels4(int row, bool valid, long long idx, const Hess4& h) {
         if (!valid) return;
         const float4 fs = frob_sq4(h);
@@ -155,11 +173,14 @@ struct StatsEpi {
         for (int o = 16; o > 0; o >>= 1) {
             m_abs = fmaxf(m_abs, __shfl_xor_sync(0xffffffffu, m_abs, o));
             m_frob = fmaxf(m_frob, __shfl_xor_sync(0xffffffffu, m_frob, o));
+            g_min = fminf(g_min, __shfl_xor_sync(0xffffffffu, g_min, o));
+            g_max = fmaxf(g_max, __shfl_xor_sync(0xffffffffu, g_max, o));
         }
         if ((threadIdx.x & 31) == 0) {
             // non-negative floats order like their bit patterns
             atomicMax((unsigned long long*)&p.hstats[NB200_HS_MAX_ABS_BITS], (unsigned long long)nb::f2u(m_abs));
             atomicMax((unsigned long long*)&p.hstats[NB200_HS_MAX_FROBSQ_BITS], (unsigned long long)nb::f2u(m_frob));
+            store_range(p.hstats, g_min, g_max);
         }
     }
 };
@@ -176,6 +197,7 @@ struct DumpEpi {
     __device__ __forceinline__ void plane(int) {}
     __device__ __forceinline__ void prefetch(int, bool, long long) {}
     __device__ __forceinline__ void cta_sync_point() {}
+    __device__ __forceinline__ void center(const float4&, const float4&) {}
     __device__ __forceinline__ void voxels4(int, bool valid, long long idx, const Hess4& h) {
         if (!valid) return;
         const float* c[6] = {&h.zz.x, &h.zy.x, &h.zx.x, &h.yy.x, &h.yx.x, &h.xx.x};
@@ -243,6 +265,7 @@ struct FrangiEpi {
         if (threadIdx.x == 0) q->n_rdy = 0;            // visible after the first barrier of the march
     }
     __device__ __forceinline__ void plane(int) {}
+    __device__ __forceinline__ void center(const float4&, const float4&) {}
     __device__ __forceinline__ void prefetch(int i, bool inb, long long idx) {
         float4 a = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
         if (inb) {
@@ -511,8 +534,9 @@ __device__ __forceinline__ ShellHessian shell_hessian(const float* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256)
-shell_stats_kernel(const float* __restrict__ g, Shell sh, nb::Spacing3 sp, StatsParams p) {
-    float m_abs = 0.0f, m_frob = 0.0f;
+shell_stats_kernel(const float* __restrict__ g, Shell sh, nb::Spacing3 sp, StatsParams p, const double* run_flag) {
+    if (run_flag != nullptr && *run_flag == 0.0) return;     // redo pass: only when the fast division was unsafe
+    float m_abs = 0.0f, m_frob = 0.0f, g_min = INFINITY, g_max = 0.0f;
     const long long total = sh.n1 + sh.n2 + sh.n3;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int zb, y, x;
@@ -523,6 +547,11 @@ shell_stats_kernel(const float* __restrict__ g, Shell sh, nb::Spacing3 sp, Stats
         m_abs = fmaxf(m_abs, fmaxf(fmaxf(fmaxf(fabsf(h.zz), fabsf(h.zy)), fmaxf(fabsf(h.zx), fabsf(h.yy))),
                                    fmaxf(fabsf(h.yx), fabsf(h.xx))));
         m_frob = fmaxf(m_frob, fs);
+        {
+            const float c = fabsf(__ldg(g + idx));
+            g_max = fmaxf(g_max, c);
+            g_min = fminf(g_min, c > 0.0f ? c : INFINITY);
+        }
         if (p.code) p.code[idx] = voxel_code(fs, h.zz, h.yy, h.xx);
         const int zg = zb + sh.v.zg_off;
         if (p.frob_samples && zg % p.sz == 0 && y % p.sy == 0 && x % p.sx == 0)
@@ -531,10 +560,21 @@ shell_stats_kernel(const float* __restrict__ g, Shell sh, nb::Spacing3 sp, Stats
     for (int o = 16; o > 0; o >>= 1) {
         m_abs = fmaxf(m_abs, __shfl_xor_sync(0xffffffffu, m_abs, o));
         m_frob = fmaxf(m_frob, __shfl_xor_sync(0xffffffffu, m_frob, o));
+        g_min = fminf(g_min, __shfl_xor_sync(0xffffffffu, g_min, o));
+        g_max = fmaxf(g_max, __shfl_xor_sync(0xffffffffu, g_max, o));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMax((unsigned long long*)&p.hstats[NB200_HS_MAX_ABS_BITS], (unsigned long long)nb::f2u(m_abs));
         atomicMax((unsigned long long*)&p.hstats[NB200_HS_MAX_FROBSQ_BITS], (unsigned long long)nb::f2u(m_frob));
+        store_range(p.hstats, g_min, g_max);
+    }
+}
+
+// redo pass: forget the maxima of the unsafe fast pass (the range words stay)
+__global__ void hstats_redo_reset_kernel(long long* hstats, const double* sp) {
+    if (threadIdx.x == 0 && sp[NB200_SP_UNSAFE] != 0.0) {
+        hstats[NB200_HS_MAX_ABS_BITS] = 0;
+        hstats[NB200_HS_MAX_FROBSQ_BITS] = 0;
     }
 }
 
@@ -699,6 +739,8 @@ nb::Spacing3 spacing3_from(const float* s) {
     for (int a = 0; a < 3; ++a) {
         sp.h1[a] = s[2 * a];
         sp.h2[a] = s[2 * a + 1];
+        sp.r1[a] = 1.0f / s[2 * a];
+        sp.r2[a] = 1.0f / s[2 * a + 1];
     }
     return sp;
 }
@@ -791,9 +833,12 @@ int launch_one(const float* g, const nb200_vol& v, const CUtensorMap& map, bool 
 
 // interior march: FAST mode enqueues the fast kernel and its IEEE twin; the device flag sp[UNSAFE] picks the
 // one that runs
+// twin: 0 = fast launch (runs unless sp[UNSAFE]) + IEEE twin (runs if sp[UNSAFE]);  1 = fast launch only,
+// unconditional (K2's first pass, which also measures the value range the flag is derived from);
+// 2 = IEEE twin only (K2's redo pass)
 template <class Epi, class Params>
 int launch_march(const float* g, const nb200_vol& v, const float* spacing, int div_mode, const double* sp,
-                 int check_skip, const Params& p, cudaStream_t st, const char* what) {
+                 int check_skip, const Params& p, cudaStream_t st, const char* what, int twin = 0) {
     const MarchPlan m = plan_march(v);
     if (m.n_ctas == 0) return NB200_OK;
     CUtensorMap map;
@@ -801,6 +846,8 @@ int launch_march(const float* g, const nb200_vol& v, const float* spacing, int d
     int rc;
     if (div_mode == hm::DIV_POW2) rc = launch_one<hm::DIV_POW2, Epi>(g, v, map, use_tma, m, spacing, sp, -1, check_skip, p, st);
     else if (div_mode == hm::DIV_IEEE || sp == nullptr) rc = launch_one<hm::DIV_IEEE, Epi>(g, v, map, use_tma, m, spacing, sp, -1, check_skip, p, st);
+    else if (twin == 1) rc = launch_one<hm::DIV_FAST, Epi>(g, v, map, use_tma, m, spacing, sp, -1, check_skip, p, st);
+    else if (twin == 2) rc = launch_one<hm::DIV_IEEE, Epi>(g, v, map, use_tma, m, spacing, sp, 1, check_skip, p, st);
     else {
         rc = launch_one<hm::DIV_FAST, Epi>(g, v, map, use_tma, m, spacing, sp, 0, check_skip, p, st);
         if (rc == NB200_OK) rc = launch_one<hm::DIV_IEEE, Epi>(g, v, map, use_tma, m, spacing, sp, 1, check_skip, p, st);
@@ -828,6 +875,8 @@ int nb200_divisor_mode(float d, int* mode_out, void* stream) {
     int e = 0;
     const float m = frexpf(d, &e);
     if (m == 0.5f && e > -60 && e < 60) { *mode_out = hm::DIV_POW2; return NB200_OK; }
+    // outside [2^-12, 2^12] the value-range argument behind sp[UNSAFE] (finalize_max_abs_kernel) does not hold
+    if (!(d >= 0.000244140625f && d <= 4096.0f)) { *mode_out = hm::DIV_IEEE; return NB200_OK; }
     cudaStream_t st = nb::as_stream(stream);
     unsigned long long* dev = nullptr;
     cudaError_t ce = cudaMalloc(&dev, sizeof(unsigned long long));   // init-time only, never on the frame path
@@ -848,9 +897,11 @@ int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* s
     return nb200_hessian_stats_code(gauss, vol, spacing, div_mode, sp, sz, sy, sx, frob_samples, hstats, nullptr, stream);
 }
 
-int nb200_hessian_stats_code(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
-                             const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
-                             float* code, void* stream) {
+namespace {
+// pass 0 = first (fast division unconditional when div_mode is FAST), pass 1 = redo with IEEE if sp[UNSAFE]
+int hessian_stats_impl(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode, const double* sp,
+                       int sz, int sy, int sx, float* frob_samples, long long* hstats, float* code, void* stream,
+                       int pass) {
     NB_REQUIRE(gauss && vol && spacing && hstats && sz > 0 && sy > 0 && sx > 0, NB200_ERR_ARG,
                "nb200_hessian_stats: bad argument");
     NB_REQUIRE(code != gauss, NB200_ERR_ARG, "nb200_hessian_stats: code must not alias the blurred volume");
@@ -859,6 +910,7 @@ int nb200_hessian_stats_code(const float* gauss, const nb200_vol* vol, const flo
     int rc = check_vol(v, "nb200_hessian_stats");
     if (rc) return rc;
     if (v.zc0 == v.zc1) return NB200_OK;
+    if (pass == 1 && (div_mode != hm::DIV_FAST || sp == nullptr)) return NB200_OK;   // nothing to redo
     StatsParams p;
     p.sz = sz; p.sy = sy; p.sx = sx;
     const int g0 = v.zc0 + v.zg_off;
@@ -870,14 +922,33 @@ int nb200_hessian_stats_code(const float* gauss, const nb200_vol* vol, const flo
     p.code = code;
     p.code_vec_ok = (v.nx % 4 == 0) && ((reinterpret_cast<unsigned long long>(code) & 15ull) == 0);
     cudaStream_t st = nb::as_stream(stream);
-    rc = launch_march<StatsEpi>(gauss, v, spacing, div_mode, sp, 0, p, st, "hessian_stats");
+    if (pass == 1) {
+        hstats_redo_reset_kernel<<<1, 32, 0, st>>>(hstats, sp);
+        rc = nb::check_launch("hessian_stats(redo reset)");
+        if (rc) return rc;
+    }
+    rc = launch_march<StatsEpi>(gauss, v, spacing, div_mode, sp, 0, p, st, "hessian_stats", pass == 0 ? 1 : 2);
     if (rc) return rc;
     const Shell sh = make_shell(v);
     if (sh.n1 + sh.n2 + sh.n3 > 0) {
-        shell_stats_kernel<<<shell_grid(sh), 256, 0, st>>>(gauss, sh, spacing3_from(spacing), p);
+        shell_stats_kernel<<<shell_grid(sh), 256, 0, st>>>(gauss, sh, spacing3_from(spacing), p,
+                                                          pass == 1 ? sp + NB200_SP_UNSAFE : nullptr);
         rc = nb::check_launch("hessian_stats(shell)");
     }
     return rc;
+}
+}  // namespace
+
+int nb200_hessian_stats_code(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
+                             const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
+                             float* code, void* stream) {
+    return hessian_stats_impl(gauss, vol, spacing, div_mode, sp, sz, sy, sx, frob_samples, hstats, code, stream, 0);
+}
+
+int nb200_hessian_stats_redo(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
+                             const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
+                             float* code, void* stream) {
+    return hessian_stats_impl(gauss, vol, spacing, div_mode, sp, sz, sy, sx, frob_samples, hstats, code, stream, 1);
 }
 
 int nb200_hessian_components(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode, float* out6,

@@ -235,6 +235,7 @@ __device__ __forceinline__ void produce_halo(Smem& s, const float* g_hi, const f
 //   void prefetch(int i, bool inb, long long idx);      // issue the loads the epilogue needs for row i of this plane
 //   void voxels4(int i, bool valid, long long idx, const Hess4&);   // called by ALL lanes of the warp
 //   void cta_sync_point();                              // called by every thread right after the plane's last barrier
+//   void center(const float4&, const float4&);          // the thread's own blurred values of this plane (range tracking)
 // idx = linear index (buffer coordinates) of the first voxel of the lane's group of four.
 template <int MODE, class Epi>
 __device__ __forceinline__ void march(Smem& s, const CUtensorMap* map, const float* __restrict__ g, const Geo& q,
@@ -295,6 +296,7 @@ __device__ __forceinline__ void march(Smem& s, const CUtensorMap* map, const flo
 #pragma unroll
         for (int i = 0; i < 2; ++i) epi.prefetch(i, row_inb[i] && col_inb, idx0 + (long long)i * q.v.nx);
         produce_gz<MODE>(g_hi, g_c, s.gz[zn], t, kz, C0, C1, c0, c1);
+        epi.center(c0, c1);                // the blurred values g(tz) of this thread's two rows
         float4 Y0, Y1;
         {
             const float4 gm = ld4(g_c + t.og0 - PITCH), gp = ld4(g_c + t.og0 + 2 * PITCH);

@@ -41,6 +41,7 @@ struct SparseParams {
     float alpha_sq, beta_sq;
     const double* spd;
     int vec_ok;
+    int div_mode;
     int nbx, nby, nbz;
 };
 
@@ -59,12 +60,21 @@ __device__ __noinline__ float eig_vesselness(float a00, float a01, float a02, fl
     return nb::vesselness3(l1, l2, l3, alpha_sq, beta_sq, gamma_sq);
 }
 
+template <int MODE>
+__device__ __forceinline__ void candidate_hessian(const SparseParams& p, long long at, long long plane, int zb, int y, int x,
+                                                  float (&h)[6]) {
+    GlobalLoad3 L{p.g + at, plane, p.v.nx};
+    const int n3[3] = {p.v.nz_glob, p.v.ny, p.v.nx};
+    nb::hessian3<GlobalLoad3, MODE>(L, zb + p.v.zg_off, y, x, n3, p.sp, h[0], h[1], h[2], h[3], h[4], h[5]);
+}
+
 __global__ void __launch_bounds__(NT, 3)
 frangi_sparse_kernel(const SparseParams p) {
     if (p.spd[NB200_SP_SKIP] != 0.0) return;            // empty mask: the sigma contributes nothing (:843-844)
     __shared__ Queues q;
     const float gamma_sq = (float)p.spd[NB200_SP_GAMMA_SQ];
     const float fs_min = (float)p.spd[NB200_SP_FROBSQ_MIN];   // mask <=> frob_sq >= fs_min (finalize_frob_kernel)
+    const int div_mode = (p.div_mode == NB200_DIV_FAST && p.spd[NB200_SP_UNSAFE] != 0.0) ? NB200_DIV_IEEE : p.div_mode;
     const nb200_vol v = p.v;
     const long long plane = (long long)v.ny * v.nx;
     const int lane = threadIdx.x & 31;
@@ -82,9 +92,10 @@ frangi_sparse_kernel(const SparseParams p) {
             const unsigned long long w = q.raw[e];
             const int zb = (int)(w >> 44), y = (int)((w >> 22) & 0x3fffffu), x = (int)(w & 0x3fffffu);
             at = (long long)zb * plane + (long long)y * v.nx + x;
-            GlobalLoad3 L{p.g + at, plane, v.nx};
-            const int n3[3] = {v.nz_glob, v.ny, v.nx};
-            nb::hessian3(L, zb + v.zg_off, y, x, n3, p.sp, h[0], h[1], h[2], h[3], h[4], h[5]);
+            // division: the verified constant-divisor sequence unless K2 flagged the value range as unsafe
+            if (div_mode == NB200_DIV_POW2) candidate_hessian<2>(p, at, plane, zb, y, x, h);
+            else if (div_mode == NB200_DIV_FAST) candidate_hessian<1>(p, at, plane, zb, y, x, h);
+            else candidate_hessian<0>(p, at, plane, zb, y, x, h);
             // margins relative to this voxel's own Frobenius norm (F^2 = frob_sq * 1.001 >= ||H||_F^2); outside the
             // range pd_margins accepts nothing is rejected
             const float fs = nb::frob_sq3(h[0], h[1], h[2], h[3], h[4], h[5]);
@@ -226,8 +237,10 @@ frangi_sparse_kernel(const SparseParams p) {
 }  // namespace
 
 extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
-                                   const float* spacing, float alpha_sq, float beta_sq, const double* sp, void* stream) {
+                                   const float* spacing, int div_mode, float alpha_sq, float beta_sq, const double* sp,
+                                   void* stream) {
     NB_REQUIRE(gauss && code && acc && vol && spacing && sp, NB200_ERR_ARG, "nb200_frangi_sparse: null argument");
+    NB_REQUIRE(div_mode >= 0 && div_mode <= 2, NB200_ERR_ARG, "nb200_frangi_sparse: div_mode %d", div_mode);
     const nb200_vol v = *vol;
     NB_REQUIRE(v.ny >= 2 && v.nx >= 2 && v.nz_glob >= 2, NB200_ERR_ARG,
                "nb200_frangi_sparse: every axis needs >= 2 samples (numpy.gradient)");
@@ -243,7 +256,11 @@ extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float*
     if (v.zc0 == v.zc1) return NB200_OK;
     SparseParams p;
     p.g = gauss; p.code = code; p.acc = acc; p.v = v;
-    for (int a = 0; a < 3; ++a) { p.sp.h1[a] = spacing[2 * a]; p.sp.h2[a] = spacing[2 * a + 1]; }
+    for (int a = 0; a < 3; ++a) {
+        p.sp.h1[a] = spacing[2 * a]; p.sp.h2[a] = spacing[2 * a + 1];
+        p.sp.r1[a] = 1.0f / spacing[2 * a]; p.sp.r2[a] = 1.0f / spacing[2 * a + 1];
+    }
+    p.div_mode = div_mode;
     p.alpha_sq = alpha_sq; p.beta_sq = beta_sq; p.spd = sp;
     p.vec_ok = (v.nx % 4 == 0) && (((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(code)) & 15) == 0);
     p.nbx = (v.nx + BX - 1) / BX;

@@ -264,6 +264,15 @@ __global__ void finalize_max_abs_kernel(const long long* hstats, double* sp) {
     float m = nb::u2f((uint32_t)hstats[NB200_HS_MAX_ABS_BITS]);
     if (!(m > 0.0f)) m = 1.0f;  // filtering.py:560-561
     sp[NB200_SP_MAX_ABS] = (double)m;
+    // Fast constant-divisor division (verified for numerators with exponent in [-90, 90] and divisors in
+    // [2^-12, 2^12]) is safe when every non-zero |g| lies in [2^-30, 2^60]: a non-zero first difference is then
+    // >= ulp(2^-30) = 2^-53 and <= 2^61, a first derivative lies in [2^-65, 2^73], and a non-zero difference of
+    // first derivatives in [ulp(2^-65), 2^74] = [2^-88, 2^74].  Otherwise the kernels redo / run with IEEE division.
+    const uint32_t compl_min = (uint32_t)hstats[NB200_HS_MIN_NZ_COMPL];
+    const float g_min = compl_min == 0u ? 1.0f : nb::u2f(0x7f800000u - compl_min);
+    const float g_max = nb::u2f((uint32_t)hstats[NB200_HS_MAX_G_BITS]);
+    const bool safe = g_min >= 9.313225746154785e-10f && g_max <= 1.152921504606847e18f;
+    sp[NB200_SP_UNSAFE] = safe ? 0.0 : 1.0;
 }
 
 __global__ void finalize_frob_kernel(const long long* state, const long long* hstats, double fixed_thresh,

@@ -298,6 +298,12 @@ class FrangiEngine3D:
                        sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), _ptr(code), st)
             self.reduce_hstats(self.hstats)
             self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
+            if self.div_mode == _cabi.DIV_FAST:
+                # safety net of the fast division: kernels that return at once unless sp[UNSAFE] was just set
+                self._call("nb200_hessian_stats_redo", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
+                           sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), _ptr(code), st)
+                self.reduce_hstats(self.hstats)
+                self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
             # F5: Frobenius threshold
             fixed = float("nan") if self.p.frob_thresh is None else float(self.p.frob_thresh)
             division = float(self.p.frob_thresh_division or 0.0)
@@ -310,7 +316,7 @@ class FrangiEngine3D:
             # F4-F9 fused
             if self.sparse_k3:
                 self._call("nb200_frangi_sparse", _ptr(g), _ptr(code), _ptr(self.acc), C.byref(own), self._fd_c,
-                           float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
+                           self.div_mode, float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
             else:
                 self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode,
                            float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)

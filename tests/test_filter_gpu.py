@@ -204,3 +204,31 @@ def test_sparse_k3_on_odd_shape_and_fresh_phantom():
         assert np.array_equal(got > 0, ref > 0)
         assert frangi_tolerance(got, ref).all()
         print(shape, "bit mismatches:", int((got != ref).sum()))
+
+
+def test_fast_division_safety_net():
+    """The verified constant-divisor division is only used while every non-zero blurred value lies in
+    [2^-30, 2^60] (sp[UNSAFE], thresholds.cu); a frame of tiny values must take the IEEE redo path and still
+    match the oracle, a normal frame must not."""
+    import torch
+    from nellie_b200 import _cabi
+    from nellie_b200.engine import FilterParams, FrangiEngine3D
+    from nellie_b200.phantoms import tubular_phantom_np
+    from oracle import pipeline as P
+    dim_res = {"X": 0.1, "Y": 0.1, "Z": 0.1, "T": 1.0}
+    shape = (24, 44, 64)
+    raw = tubular_phantom_np(shape, seed=21, n_tubes=5)
+    eng = FrangiEngine3D(shape, FilterParams(dim_res=dim_res), device="cuda")
+    assert eng.div_mode == _cabi.DIV_FAST
+    for scale, want_unsafe in [(1.0, 0.0), (1e-12, 1.0)]:
+        x = (raw * np.float32(scale)).astype(np.float32)
+        got = eng.filter_frame(torch.from_numpy(x).cuda()).cpu().numpy()
+        rec = eng.sigma_records()
+        assert (rec[:, _cabi.SP_UNSAFE] == want_unsafe).all(), (scale, rec[:, _cabi.SP_UNSAFE])
+        ref = P.filter_frame(x, P.FrameSpec(dim_res=dim_res, no_z=False))
+        assert np.array_equal(got > 0, ref > 0), scale
+        assert frangi_tolerance(got, ref).all(), scale
+        eng.sparse_k3 = False
+        got2 = eng.filter_frame(torch.from_numpy(x).cuda()).cpu().numpy()
+        eng.sparse_k3 = True
+        assert np.array_equal(got, got2), scale
