@@ -180,6 +180,13 @@ def run_b200_arm(args):
     barrier()
     ms = e0.elapsed_time(e1)
     prof = eng.profile_summary()
+    # per-sigma average launch time of the per-sigma kernels (calls come in sigma order, once per sigma and step)
+    per_sigma = {}
+    nsig = len(SIGMAS_CFG3)
+    for name in ("nb200_gauss_axis", "nb200_gauss_yx", "nb200_hessian_stats_code", "nb200_frangi_sparse", "nb200_frangi_accumulate"):
+        evs = [(a, b) for nm, a, b in (eng.profile or []) if nm == name]
+        if evs and len(evs) % nsig == 0:
+            per_sigma[name] = [round(float(np.mean([a.elapsed_time(b) for a, b in evs[i::nsig]])), 3) for i in range(nsig)]
     eng.profile = None
     timed_launches = eng.launches
     clocks = sampler.stop() if rank == 0 else None
@@ -238,7 +245,7 @@ def run_b200_arm(args):
                                    f"{SIGMAS_CFG3}, dim_res 0.1 um isotropic" + (f", Z-sharded over {world} GPUs with halo exchange" if world > 1 else ""),
                        "l2_policy": "inputs larger than L2 (4 B x voxels per buffer >> 126 MB)", "seed": 3},
             "clocks": clocks, "e2e": e2e, "gpu_launches": timed_launches, "roofline": roofline, "cpu_baseline": cpu,
-            "kernel_ms_per_step": breakdown}
+            "kernel_ms_per_step": breakdown, "kernel_ms_per_sigma": per_sigma}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

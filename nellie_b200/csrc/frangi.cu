@@ -79,6 +79,24 @@ __device__ __noinline__ float2 eig_vesselness_pair(H6 a, H6 b, float alpha_sq, f
     return r;
 }
 
+// voxel_code of 4 voxels on the packed pipes (same arithmetic: every sum / product rounded once)
+__device__ __forceinline__ float2 voxel_code2(float2 fs, float2 zz, float2 yy, float2 xx) {
+    const float2 a = hm::add2(zz, yy), b = hm::add2(zz, xx), c = hm::add2(yy, xx);
+    const float2 m = make_float2(fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y));
+    const float2 mm = __fmul2_rn(m, m), lim = __fmul2_rn(make_float2(1.001e-10f, 1.001e-10f), fs);
+    const bool z0 = m.x > 0.0f && mm.x > lim.x && fs.x > 1e-20f && fs.x < 1e20f;
+    const bool z1 = m.y > 0.0f && mm.y > lim.y && fs.y > 1e-20f && fs.y < 1e20f;
+    return make_float2(z0 ? __uint_as_float(__float_as_uint(fs.x) | 0x80000000u) : fs.x,
+                       z1 ? __uint_as_float(__float_as_uint(fs.y) | 0x80000000u) : fs.y);
+}
+__device__ __forceinline__ float4 voxel_code4(const float4& fs, const Hess4& h) {
+    const float2 lo = voxel_code2(make_float2(fs.x, fs.y), make_float2(h.zz.x, h.zz.y), make_float2(h.yy.x, h.yy.y),
+                                  make_float2(h.xx.x, h.xx.y));
+    const float2 hi = voxel_code2(make_float2(fs.z, fs.w), make_float2(h.zz.z, h.zz.w), make_float2(h.yy.z, h.yy.w),
+                                  make_float2(h.xx.z, h.xx.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 // --------------------------------------------------------------------------------------------
 // epilogues of the interior march
 // --------------------------------------------------------------------------------------------
@@ -156,8 +174,7 @@ struct StatsEpi {
                                    fmaxf(absmax4(h.yx), absmax4(h.xx))));
         m_frob = fmaxf(m_frob, fmaxf(fmaxf(fs.x, fs.y), fmaxf(fs.z, fs.w)));
         if (p.code) {
-            const float4 c = make_float4(voxel_code(fs.x, h.zz.x, h.yy.x, h.xx.x), voxel_code(fs.y, h.zz.y, h.yy.y, h.xx.y),
-                                         voxel_code(fs.z, h.zz.z, h.yy.z, h.xx.z), voxel_code(fs.w, h.zz.w, h.yy.w, h.xx.w));
+            const float4 c = voxel_code4(fs, h);
             if (p.code_vec_ok) *reinterpret_cast<float4*>(p.code + idx) = c;
             else { p.code[idx] = c.x; p.code[idx + 1] = c.y; p.code[idx + 2] = c.z; p.code[idx + 3] = c.w; }
         }

@@ -60,12 +60,55 @@ __device__ __noinline__ float eig_vesselness(float a00, float a01, float a02, fl
     return nb::vesselness3(l1, l2, l3, alpha_sq, beta_sq, gamma_sq);
 }
 
+// (a - b) / fl32(2h) of one axis
+template <int MODE>
+__device__ __forceinline__ float cdiff(float a, float b, float d, float r) {
+    const float n = a - b;
+    if (MODE == 2) return n * r;
+    if (MODE == 1) {
+        const float q0 = n * r;
+        const float e = fmaf(-q0, d, n);
+        return fmaf(e, r, q0);
+    }
+    return n / d;
+}
+
 template <int MODE>
 __device__ __forceinline__ void candidate_hessian(const SparseParams& p, long long at, long long plane, int zb, int y, int x,
                                                   float (&h)[6]) {
-    GlobalLoad3 L{p.g + at, plane, p.v.nx};
-    const int n3[3] = {p.v.nz_glob, p.v.ny, p.v.nx};
-    nb::hessian3<GlobalLoad3, MODE>(L, zb + p.v.zg_off, y, x, n3, p.sp, h[0], h[1], h[2], h[3], h[4], h[5]);
+    const int zg = zb + p.v.zg_off;
+    const int nx = p.v.nx;
+    if (zg >= 2 && zg < p.v.nz_glob - 2 && y >= 2 && y < p.v.ny - 2 && x >= 2 && x < nx - 2) {
+        // interior: central differences only (19 distinct samples, fixed offsets); same operations in the same
+        // order as nb::hessian3 / numpy.gradient(numpy.gradient(g))
+        const float* c = p.g + at;
+        const long long P = plane;
+        const float dz = p.sp.h2[0], dy = p.sp.h2[1], dx = p.sp.h2[2];
+        const float rz = p.sp.r2[0], ry = p.sp.r2[1], rx = p.sp.r2[2];
+        const float g0 = __ldg(c);
+        const float zp2 = __ldg(c + 2 * P), zm2 = __ldg(c - 2 * P);
+        const float yp2 = __ldg(c + 2 * nx), ym2 = __ldg(c - 2 * nx);
+        const float xp2 = __ldg(c + 2), xm2 = __ldg(c - 2);
+        const float zpyp = __ldg(c + P + nx), zpym = __ldg(c + P - nx), zmyp = __ldg(c - P + nx), zmym = __ldg(c - P - nx);
+        const float zpxp = __ldg(c + P + 1), zpxm = __ldg(c + P - 1), zmxp = __ldg(c - P + 1), zmxm = __ldg(c - P - 1);
+        const float ypxp = __ldg(c + nx + 1), ypxm = __ldg(c + nx - 1), ymxp = __ldg(c - nx + 1), ymxm = __ldg(c - nx - 1);
+        // d0 d0: gz(z+1) - gz(z-1)
+        h[0] = cdiff<MODE>(cdiff<MODE>(zp2, g0, dz, rz), cdiff<MODE>(g0, zm2, dz, rz), dz, rz);
+        // d1 d0: gz(y+1) - gz(y-1)
+        h[1] = cdiff<MODE>(cdiff<MODE>(zpyp, zmyp, dz, rz), cdiff<MODE>(zpym, zmym, dz, rz), dy, ry);
+        // d2 d0: gz(x+1) - gz(x-1)
+        h[2] = cdiff<MODE>(cdiff<MODE>(zpxp, zmxp, dz, rz), cdiff<MODE>(zpxm, zmxm, dz, rz), dx, rx);
+        // d1 d1
+        h[3] = cdiff<MODE>(cdiff<MODE>(yp2, g0, dy, ry), cdiff<MODE>(g0, ym2, dy, ry), dy, ry);
+        // d2 d1: gy(x+1) - gy(x-1)
+        h[4] = cdiff<MODE>(cdiff<MODE>(ypxp, ymxp, dy, ry), cdiff<MODE>(ypxm, ymxm, dy, ry), dx, rx);
+        // d2 d2
+        h[5] = cdiff<MODE>(cdiff<MODE>(xp2, g0, dx, rx), cdiff<MODE>(g0, xm2, dx, rx), dx, rx);
+        return;
+    }
+    GlobalLoad3 L{p.g + at, plane, nx};
+    const int n3[3] = {p.v.nz_glob, p.v.ny, nx};
+    nb::hessian3<GlobalLoad3, MODE>(L, zg, y, x, n3, p.sp, h[0], h[1], h[2], h[3], h[4], h[5]);
 }
 
 __global__ void __launch_bounds__(NT, 3)
