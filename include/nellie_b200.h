@@ -188,7 +188,11 @@ int nb200_frangi_accumulate(const float* gauss, float* acc, const nb200_vol* vol
  * bit-identical to nb200_frangi_accumulate. */
 int nb200_frangi_sparse(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
                         const float* spacing, int div_mode, float alpha_sq, float beta_sq, const double* sp,
-                        void* stream);
+                        unsigned* list, long long list_capacity, unsigned long long* counter, void* stream);
+/*   list / counter (optional scratch): device buffer of `list_capacity` uint32 (>= voxels of [zc0,zc1)) and one
+ *   device uint64.  With them (and a buffer below 2^32 voxels) the step runs as a barrier-free stream kernel that
+ *   appends the candidates to the list plus a solve kernel that walks it; without, as one kernel with
+ *   shared-memory queues.  Same results either way. */
 /* 2-D variant (closed-form 2x2 eigenvalues, filtering.py:676-690, :737-741); spacing[4] = y,x */
 int nb200_frangi_accumulate_2d(const float* gauss, float* acc, int ny, int nx, const float* spacing,
                                float beta_sq, const double* sp, void* stream);

@@ -62,7 +62,8 @@ _SIGS = {
                                   _p, _p], C.c_int),
     "nb200_hessian_stats_redo": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p,
                                   _p, _p], C.c_int),
-    "nb200_frangi_sparse": ([_p, _p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, _p, _p], C.c_int),
+    "nb200_frangi_sparse": ([_p, _p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, _p, _p, _ll, _p, _p],
+                            C.c_int),
     "nb200_hessian_components": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, _p], C.c_int),
     "nb200_divisor_mode": ([C.c_float, C.POINTER(C.c_int), _p], C.c_int),
     "nb200_hstats_reset": ([_p, _p], C.c_int),

@@ -277,10 +277,175 @@ frangi_sparse_kernel(const SparseParams p) {
     drain(true);
 }
 
+// --------------------------------------------------------------------------------------------
+// Two-kernel form (used when the caller lends a candidate list: one uint32 per voxel of capacity).
+//   stream:  code + acc -> deaths written back, candidates appended to a global list.  No barrier anywhere:
+//            every warp stages its candidates in its own shared-memory slice and flushes 128 at a time with
+//            one global atomicAdd, so the kernel is a pure HBM stream (12 B/voxel) at high occupancy.
+//   solve:   warps walk the list 32 candidates at a time: Hessian + full zero test, survivors compacted into a
+//            per-warp queue, eigenvalues + vesselness for full warps of survivors.  No CTA barrier either.
+// The list order depends on scheduling; results do not (every voxel is independent and owns its acc word).
+// --------------------------------------------------------------------------------------------
+constexpr int WSTAGE = 256;                 // per-warp staging slots (flush at >= 128, at most 128 pushed per step)
+
+__global__ void __launch_bounds__(NT)
+sparse_stream_kernel(const SparseParams p, unsigned* __restrict__ list, unsigned long long* __restrict__ counter) {
+    if (p.spd[NB200_SP_SKIP] != 0.0) return;
+    __shared__ unsigned stage[NT / 32][WSTAGE];
+    const float fs_min = (float)p.spd[NB200_SP_FROBSQ_MIN];
+    const nb200_vol v = p.v;
+    const long long plane = (long long)v.ny * v.nx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned* mine = stage[warp];
+    int n_st = 0;                                        // warp-uniform
+    auto flush = [&](int keep_below) {
+        // write stage[0, n_st) out when it holds at least keep_below entries
+        if (n_st >= keep_below && n_st > 0) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)n_st);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            __syncwarp();
+            for (int i = lane; i < n_st; i += 32) list[base + i] = mine[i];
+            __syncwarp();
+            n_st = 0;
+        }
+    };
+    const int tx = 4 * lane;
+    const long long nbricks = (long long)p.nbx * p.nby * p.nbz;
+    for (long long b = blockIdx.x; b < nbricks; b += gridDim.x) {
+        long long r = b;
+        const int bx = (int)(r % p.nbx); r /= p.nbx;
+        const int by = (int)(r % p.nby); r /= p.nby;
+        const int x = bx * BX + tx, y = by * BY + warp;   // one row of the brick per warp
+        const int z0 = v.zc0 + (int)r * BZ;
+        const int z1 = min(z0 + BZ, v.zc1);
+        const bool row_in = y < v.ny && x < v.nx;
+        constexpr int G = 4;                             // planes in flight per thread
+        for (int zg0 = z0; zg0 < z1; zg0 += G) {
+            float4 c[G], a[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const int zb = zg0 + i;
+                c[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                a[i] = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
+                if (row_in && zb < z1) {
+                    const long long at = (long long)zb * plane + (long long)y * v.nx + x;
+                    if (p.vec_ok) {
+                        c[i] = __ldg(reinterpret_cast<const float4*>(p.code + at));
+                        a[i] = *reinterpret_cast<const float4*>(p.acc + at);
+                    } else {
+                        float* cc = &c[i].x; float* aa = &a[i].x;
+                        for (int k = 0; k < 4; ++k)
+                            if (x + k < v.nx) { cc[k] = __ldg(p.code + at + k); aa[k] = p.acc[at + k]; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const int zb = zg0 + i;
+                const float* cc = &c[i].x;
+                float* aa = &a[i].x;
+                unsigned cand = 0, kill = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool alive = aa[k] >= 0.0f;
+                    const bool pass = fabsf(cc[k]) >= fs_min;            // NaN fails, like the reference's comparison
+                    if (alive && !pass) { kill |= 1u << k; aa[k] = -1.0f; }   // dead voxels stay dead (AND of masks)
+                    if (alive && pass && !(__float_as_uint(cc[k]) >> 31)) cand |= 1u << k;
+                }
+                const long long at = (long long)zb * plane + (long long)y * v.nx + x;
+                if (kill) {
+                    if (p.vec_ok) *reinterpret_cast<float4*>(p.acc + at) = a[i];
+                    else for (int k = 0; k < 4; ++k) if ((kill >> k) & 1u) p.acc[at + k] = -1.0f;
+                }
+                if (__any_sync(0xffffffffu, cand != 0u)) {
+                    const unsigned b0 = __ballot_sync(0xffffffffu, cand & 1u), b1 = __ballot_sync(0xffffffffu, cand & 2u);
+                    const unsigned b2 = __ballot_sync(0xffffffffu, cand & 4u), b3 = __ballot_sync(0xffffffffu, cand & 8u);
+                    const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
+                    const unsigned at32 = (unsigned)at;
+                    if (cand & 1u) mine[n_st + __popc(b0 & lt)] = at32;
+                    if (cand & 2u) mine[n_st + n0 + __popc(b1 & lt)] = at32 + 1u;
+                    if (cand & 4u) mine[n_st + n0 + n1 + __popc(b2 & lt)] = at32 + 2u;
+                    if (cand & 8u) mine[n_st + n0 + n1 + n2 + __popc(b3 & lt)] = at32 + 3u;
+                    n_st += n0 + n1 + n2 + n3;
+                    flush(WSTAGE - 128);
+                }
+            }
+        }
+    }
+    flush(1);
+}
+
+constexpr int WQ = 64;                      // per-warp survivor queue (< 32 left over + <= 32 pushed)
+
+__global__ void __launch_bounds__(NT, 3)
+sparse_solve_kernel(const SparseParams p, const unsigned* __restrict__ list, const unsigned long long* __restrict__ counter) {
+    if (p.spd[NB200_SP_SKIP] != 0.0) return;
+    __shared__ float wq[NT / 32][7][WQ];
+    const float gamma_sq = (float)p.spd[NB200_SP_GAMMA_SQ];
+    const int div_mode = (p.div_mode == NB200_DIV_FAST && p.spd[NB200_SP_UNSAFE] != 0.0) ? NB200_DIV_IEEE : p.div_mode;
+    const nb200_vol v = p.v;
+    const unsigned plane = (unsigned)((long long)v.ny * v.nx), nx = (unsigned)v.nx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    float (*q)[WQ] = wq[warp];
+    int n_q = 0;                                         // warp-uniform
+    const unsigned long long n = *counter;
+    const unsigned long long wstride = (unsigned long long)gridDim.x * (NT / 32) * 32ull;
+    auto solve32 = [&](int cnt) {                        // the top `cnt` (<= 32) entries of this warp's queue
+        __syncwarp();
+        const int e = n_q - cnt + lane;
+        if (lane < cnt) {
+            const unsigned at = __float_as_uint(q[6][e]);
+            const float cur = p.acc[at];
+            const float vv = eig_vesselness(q[0][e], q[1][e], q[2][e], q[3][e], q[4][e], q[5][e], p.alpha_sq, p.beta_sq, gamma_sq);
+            if (vv > cur) p.acc[at] = vv;                // acc >= 0 here: a zero response changes nothing
+        }
+        n_q -= cnt;
+        __syncwarp();
+    };
+    for (unsigned long long base = ((unsigned long long)blockIdx.x * (NT / 32) + warp) * 32ull; base < n; base += wstride) {
+        const unsigned long long i = base + lane;
+        bool keep = false;
+        float h[6];
+        unsigned at = 0;
+        if (i < n) {
+            at = list[i];
+            const unsigned zb = at / plane, rem = at - zb * plane;
+            const unsigned y = rem / nx, x = rem - y * nx;
+            if (div_mode == NB200_DIV_POW2) candidate_hessian<2>(p, (long long)at, (long long)plane, (int)zb, (int)y, (int)x, h);
+            else if (div_mode == NB200_DIV_FAST) candidate_hessian<1>(p, (long long)at, (long long)plane, (int)zb, (int)y, (int)x, h);
+            else candidate_hessian<0>(p, (long long)at, (long long)plane, (int)zb, (int)y, (int)x, h);
+            const float fs = nb::frob_sq3(h[0], h[1], h[2], h[3], h[4], h[5]);
+            float tau2 = INFINITY, tau3 = INFINITY;
+            if (fs > 1e-20f && fs < 1e20f) {
+                const float f2 = 1.001f * fs;
+                tau2 = 1e-5f * f2;
+                tau3 = 1e-4f * (f2 * sqrtf(f2));
+            }
+            keep = !nb::pd_reject_full(h[0], h[1], h[2], h[3], h[4], h[5], tau2, tau3);
+        }
+        const unsigned bits = __ballot_sync(0xffffffffu, keep);
+        if (bits != 0u) {
+            if (keep) {
+                const int o = n_q + __popc(bits & lt);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) q[j][o] = h[j];
+                q[6][o] = __uint_as_float(at);
+            }
+            n_q += __popc(bits);
+            if (n_q >= 32) solve32(32);
+        }
+    }
+    if (n_q > 0) solve32(n_q);
+}
+
 }  // namespace
 
 extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
                                    const float* spacing, int div_mode, float alpha_sq, float beta_sq, const double* sp,
+                                   unsigned* list, long long list_capacity, unsigned long long* counter,
                                    void* stream) {
     NB_REQUIRE(gauss && code && acc && vol && spacing && sp, NB200_ERR_ARG, "nb200_frangi_sparse: null argument");
     NB_REQUIRE(div_mode >= 0 && div_mode <= 2, NB200_ERR_ARG, "nb200_frangi_sparse: div_mode %d", div_mode);
@@ -310,6 +475,19 @@ extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float*
     p.nby = (v.ny + BY - 1) / BY;
     p.nbz = (v.zc1 - v.zc0 + BZ - 1) / BZ;
     const long long nbricks = (long long)p.nbx * p.nby * p.nbz;
+    const long long n_own = (long long)(v.zc1 - v.zc0) * v.ny * v.nx;
+    const long long n_buf = (long long)v.nz_buf * v.ny * v.nx;
+    if (list != nullptr && counter != nullptr && list_capacity >= n_own && n_buf < (1LL << 32)) {
+        cudaStream_t st = nb::as_stream(stream);
+        cudaError_t ce = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+        NB_REQUIRE(ce == cudaSuccess, NB200_ERR_CUDA, "nb200_frangi_sparse: %s", cudaGetErrorString(ce));
+        const long long cap_s = 8LL * nb::sm_count();
+        sparse_stream_kernel<<<(unsigned)(nbricks < cap_s ? nbricks : cap_s), NT, 0, st>>>(p, list, counter);
+        int rc = nb::check_launch("frangi_sparse(stream)");
+        if (rc) return rc;
+        sparse_solve_kernel<<<(unsigned)(3 * nb::sm_count()), NT, 0, st>>>(p, list, counter);
+        return nb::check_launch("frangi_sparse(solve)");
+    }
     const long long cap = 3LL * nb::sm_count();
     frangi_sparse_kernel<<<(unsigned)(nbricks < cap ? nbricks : cap), NT, 0, nb::as_stream(stream)>>>(p);
     return nb::check_launch("frangi_sparse");

@@ -182,6 +182,8 @@ class FrangiEngine3D:
         self.fd = params.fd_spacing_f32()
         self._fd_c = self.fd.ctypes.data_as(C.POINTER(C.c_float))
         self.div_mode = self._pick_div_mode()
+        self.sparse_list = True  # sparse K3 as stream + solve kernels over a global candidate list (else: one kernel, smem queues)
+        self.list_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.sparse_k3 = True  # K3 from K2's per-voxel record (nb200_frangi_sparse); False = dense march (nb200_frangi_accumulate)
         self.fuse_yx = True   # Y and X blur passes in one kernel (nb200_gauss_yx); False = one kernel per axis
         self.launches = 0
@@ -315,8 +317,11 @@ class FrangiEngine3D:
             self._call("nb200_finalize_frob", _ptr(self.hist), _ptr(self.hstats), fixed, division, _ptr(sp_i), st)
             # F4-F9 fused
             if self.sparse_k3:
+                # candidate list: the output volume is idle until finalize() and holds one word per owned voxel
+                lst = self.out if self.sparse_list else None
                 self._call("nb200_frangi_sparse", _ptr(g), _ptr(code), _ptr(self.acc), C.byref(own), self._fd_c,
-                           self.div_mode, float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
+                           self.div_mode, float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i),
+                           _ptr(lst), self.out.numel(), _ptr(self.list_count), st)
             else:
                 self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode,
                            float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
