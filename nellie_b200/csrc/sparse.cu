@@ -15,6 +15,8 @@
 //   RDY (six entries + index)  survivors; drained 256 at a time by the eigen-solver + vesselness.
 // Both expensive phases run with full warps whatever the shape of the mask.
 // Algorithmic HBM traffic: 12 B/voxel (code R, acc R, acc W) + the blurred neighbourhoods of the candidates.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "hessian.cuh"
 
@@ -481,7 +483,10 @@ extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float*
         cudaStream_t st = nb::as_stream(stream);
         cudaError_t ce = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
         NB_REQUIRE(ce == cudaSuccess, NB200_ERR_CUDA, "nb200_frangi_sparse: %s", cudaGetErrorString(ce));
-        const long long cap_s = 8LL * nb::sm_count();
+        // few resident bricks: the list then walks the volume in compact order and the solve kernel's stencil
+        // reads stay inside L2 (with 8 CTAs/SM the candidates of > 1000 bricks interleave and DRAM reads triple)
+        static const int per_sm = getenv("NB200_STREAM_CTAS") ? atoi(getenv("NB200_STREAM_CTAS")) : 3;
+        const long long cap_s = (long long)(per_sm > 0 ? per_sm : 3) * nb::sm_count();
         sparse_stream_kernel<<<(unsigned)(nbricks < cap_s ? nbricks : cap_s), NT, 0, st>>>(p, list, counter);
         int rc = nb::check_launch("frangi_sparse(stream)");
         if (rc) return rc;
