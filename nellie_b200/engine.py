@@ -186,7 +186,8 @@ class FrangiEngine3D:
         self.list_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.sparse_k3 = True  # K3 from K2's per-voxel record (nb200_frangi_sparse); False = dense march (nb200_frangi_accumulate)
         self.fuse_yx = True   # Y and X blur passes in one kernel (nb200_gauss_yx); False = one kernel per axis
-        self.launches = 0
+        self.launches = 0     # C-ABI calls
+        self.kernels = 0      # CUDA kernels enqueued by those calls
         self.profile = None   # set to a list to record (name, start, end) CUDA events per C-ABI call
         # hooks for the multi-GPU driver (identity on one GPU)
         self.exchange_halo = lambda buf, depth: None
@@ -219,8 +220,14 @@ class FrangiEngine3D:
         zc1 = self.pad_lo + self.nz_own + min(extra_hi, self.pad_hi)
         return Vol(self.nz_buf, self.ny, self.nx, zc0, zc1, self.zg_off, self.nz_glob)
 
+    # CUDA kernels behind one C-ABI call (default 1): K2 = march + border shell, redo = reset + IEEE twin + shell,
+    # sparse K3 = stream + solve, dense K3 = march + IEEE twin + shell, percentile = radix select passes
+    KERNELS_PER_CALL = {"nb200_hessian_stats_code": 2, "nb200_hessian_stats_redo": 3, "nb200_frangi_sparse": 2,
+                        "nb200_frangi_accumulate": 3, "nb200_percentile": 17}
+
     def _call(self, name, *args):
         self.launches += 1
+        self.kernels += self.KERNELS_PER_CALL.get(name, 1)
         if self.profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
