@@ -235,3 +235,34 @@ def test_fast_division_safety_net():
         got2 = eng.filter_frame(torch.from_numpy(x).cuda()).cpu().numpy()
         eng.sparse_k3 = True
         assert np.array_equal(got, got2), scale
+
+
+def test_filter_and_label_run_on_ome_tiff_files(tmp_path):
+    """nellie.run-level flow on real files (run.py:56-73): necessities OME-TIFF -> Filter.run() -> im_preprocessed
+    (float32) -> Label.run() -> im_instance_label (int32), through nellie_b200.imio's memmaps; what lands on disk
+    must equal the oracle's frames."""
+    from nellie_b200 import Filter, Label, imio
+    from nellie_b200.phantoms import tubular_phantom_np
+    from oracle import pipeline as P
+    dim_res = {"X": 0.1, "Y": 0.1, "Z": 0.2, "T": 1.0}
+    frames = np.stack([tubular_phantom_np((20, 48, 64), seed=500 + t, n_tubes=5) for t in range(3)])
+    frames = np.clip(frames, 0, 60000).astype(np.uint16)
+    info = imio.StackInfo.from_array(frames, "TZYX", dim_res, str(tmp_path), "phantom")
+    Filter(info, device="b200").run()
+    pre = imio.read_tiff(info.pipeline_paths["im_preprocessed"])
+    assert pre.dtype == np.float32 and pre.shape == frames.shape
+    Label(info, device="b200").run()
+    lab = imio.read_tiff(info.pipeline_paths["im_instance_label"])
+    assert lab.dtype == np.int32 and lab.shape == frames.shape
+    spec = P.FrameSpec(dim_res=dim_res, no_z=False)
+    for t in range(3):
+        ref, ref_lab = P.segment_frame(frames[t], spec)
+        assert np.array_equal(pre[t] > 0, ref > 0), t
+        assert frangi_tolerance(pre[t], ref).all(), t
+        assert lab[t].max() >= 1 and lab[t].min() == 0
+        # label ids are exact given the same threshold; the device threshold agrees to ~1e-7 relative (log10f vs
+        # numpy's SIMD log10, DESIGN.md section 3), so allow a voxel on the knife edge
+        bad = int((lab[t] != ref_lab).sum())
+        assert bad <= max(1, lab[t].size // 100000), (t, bad)
+        assert lab[t].max() == ref_lab.max()
+    assert np.array_equal(imio.read_tiff(info.im_path), frames), "raw stack was modified"
