@@ -113,11 +113,30 @@ opening_march_kernel(const float* __restrict__ acc, float* __restrict__ out, nb2
             }
         return;
     }
-    // p = incoming mask plane; erosion lags one plane, the output two
+    // p = incoming mask plane; erosion lags one plane, the output two.  The rows of plane p+1 are requested while
+    // plane p is processed (register double buffer), so no barrier ever waits for global memory.
+    constexpr int RPL = (ROWS + NW - 1) / NW;               // mask rows per warp
+    float4 nxt[RPL];
+    auto fetch_rows = [&](int pl, float4 (&t)[RPL]) {
+        const int pg = pl + v.zg_off;
+        const bool z_in = pg >= 0 && pg < v.nz_glob && pl >= 0 && pl < v.nz_buf;
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+            const int r = warp + NW * i, y = yw + r;
+            // out-of-frame voxels are 0 bits whatever the threshold: -inf never exceeds it
+            t[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (r < ROWS && z_in && x_in && y >= 0 && y < v.ny)
+                t[i] = __ldg(reinterpret_cast<const float4*>(acc + (long long)pl * plane + (long long)y * v.nx + x));
+        }
+    };
+    fetch_rows(zs - 2, nxt);
     for (int p = zs - 2; p <= ze + 1; ++p) {
         const int zo = p - 2;                               // output plane of this step
         const bool do_out = zo >= zs;
-        float4 cur[RPW];
+        float4 cur[RPW], now[RPL];
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) now[i] = nxt[i];
+        if (p + 1 <= ze + 1) fetch_rows(p + 1, nxt);
         if (do_out) {
 #pragma unroll
             for (int i = 0; i < RPW; ++i) {
@@ -129,20 +148,18 @@ opening_march_kernel(const float* __restrict__ acc, float* __restrict__ out, nb2
         }
         // ---- phase 1: bits of plane p ----
         {
-            const int pg = p + v.zg_off;
-            const bool z_in = pg >= 0 && pg < v.nz_glob && p >= 0 && p < v.nz_buf;
             unsigned (*mp)[4] = m[(p + 3) % 3];
-            for (int r = warp; r < ROWS; r += NW) {
-                const int y = yw + r;
-                float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);      // 0 > cut is false for cut >= 0 ...
-                const bool ok = z_in && x_in && y >= 0 && y < v.ny;
-                if (ok) a = __ldg(reinterpret_cast<const float4*>(acc + (long long)p * plane + (long long)y * v.nx + x));
-                // ... but be explicit: out-of-frame voxels are 0 bits whatever the threshold
-                const unsigned w0 = __ballot_sync(0xffffffffu, ok && a.x > cut);
-                const unsigned w1 = __ballot_sync(0xffffffffu, ok && a.y > cut);
-                const unsigned w2 = __ballot_sync(0xffffffffu, ok && a.z > cut);
-                const unsigned w3 = __ballot_sync(0xffffffffu, ok && a.w > cut);
-                if (lane == 0) *reinterpret_cast<uint4*>(mp[r]) = make_uint4(w0, w1, w2, w3);
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) {
+                const int r = warp + NW * i;
+                if (r < ROWS) {                              // warp-uniform
+                    const float4 a = now[i];
+                    const unsigned w0 = __ballot_sync(0xffffffffu, a.x > cut);
+                    const unsigned w1 = __ballot_sync(0xffffffffu, a.y > cut);
+                    const unsigned w2 = __ballot_sync(0xffffffffu, a.z > cut);
+                    const unsigned w3 = __ballot_sync(0xffffffffu, a.w > cut);
+                    if (lane == 0) *reinterpret_cast<uint4*>(mp[r]) = make_uint4(w0, w1, w2, w3);
+                }
             }
         }
         __syncthreads();

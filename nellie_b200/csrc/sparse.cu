@@ -45,6 +45,7 @@ struct SparseParams {
     int vec_ok;
     int div_mode;
     int nbx, nby, nbz;
+    int bz;                 // brick depth in planes
 };
 
 struct GlobalLoad3 {
@@ -320,8 +321,8 @@ sparse_stream_kernel(const SparseParams p, unsigned* __restrict__ list, unsigned
         const int bx = (int)(r % p.nbx); r /= p.nbx;
         const int by = (int)(r % p.nby); r /= p.nby;
         const int x = bx * BX + tx, y = by * BY + warp;   // one row of the brick per warp
-        const int z0 = v.zc0 + (int)r * BZ;
-        const int z1 = min(z0 + BZ, v.zc1);
+        const int z0 = v.zc0 + (int)r * p.bz;
+        const int z1 = min(z0 + p.bz, v.zc1);
         const bool row_in = y < v.ny && x < v.nx;
         constexpr int G = 4;                             // planes in flight per thread
         for (int zg0 = z0; zg0 < z1; zg0 += G) {
@@ -475,8 +476,9 @@ extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float*
     p.vec_ok = (v.nx % 4 == 0) && (((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(code)) & 15) == 0);
     p.nbx = (v.nx + BX - 1) / BX;
     p.nby = (v.ny + BY - 1) / BY;
+    p.bz = BZ;
     p.nbz = (v.zc1 - v.zc0 + BZ - 1) / BZ;
-    const long long nbricks = (long long)p.nbx * p.nby * p.nbz;
+    long long nbricks = (long long)p.nbx * p.nby * p.nbz;
     const long long n_own = (long long)(v.zc1 - v.zc0) * v.ny * v.nx;
     const long long n_buf = (long long)v.nz_buf * v.ny * v.nx;
     if (list != nullptr && counter != nullptr && list_capacity >= n_own && n_buf < (1LL << 32)) {
@@ -486,6 +488,10 @@ extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float*
         // few resident bricks: the list then walks the volume in compact order and the solve kernel's stencil
         // reads stay inside L2 (with 8 CTAs/SM the candidates of > 1000 bricks interleave and DRAM reads triple)
         static const int per_sm = getenv("NB200_STREAM_CTAS") ? atoi(getenv("NB200_STREAM_CTAS")) : 3;
+        static const int bz_s = getenv("NB200_STREAM_BZ") ? atoi(getenv("NB200_STREAM_BZ")) : 16;
+        p.bz = bz_s > 0 ? bz_s : 16;
+        p.nbz = (v.zc1 - v.zc0 + p.bz - 1) / p.bz;
+        nbricks = (long long)p.nbx * p.nby * p.nbz;
         const long long cap_s = (long long)(per_sm > 0 ? per_sm : 3) * nb::sm_count();
         sparse_stream_kernel<<<(unsigned)(nbricks < cap_s ? nbricks : cap_s), NT, 0, st>>>(p, list, counter);
         int rc = nb::check_launch("frangi_sparse(stream)");
@@ -493,6 +499,9 @@ extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float*
         sparse_solve_kernel<<<(unsigned)(3 * nb::sm_count()), NT, 0, st>>>(p, list, counter);
         return nb::check_launch("frangi_sparse(solve)");
     }
+    p.bz = BZ;
+    p.nbz = (v.zc1 - v.zc0 + BZ - 1) / BZ;
+    nbricks = (long long)p.nbx * p.nby * p.nbz;
     const long long cap = 3LL * nb::sm_count();
     frangi_sparse_kernel<<<(unsigned)(nbricks < cap ? nbricks : cap), NT, 0, nb::as_stream(stream)>>>(p);
     return nb::check_launch("frangi_sparse");
