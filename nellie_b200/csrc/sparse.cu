@@ -382,7 +382,7 @@ sparse_stream_kernel(const SparseParams p, unsigned* __restrict__ list, unsigned
 
 constexpr int WQ = 64;                      // per-warp survivor queue (< 32 left over + <= 32 pushed)
 
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, 4)
 sparse_solve_kernel(const SparseParams p, const unsigned* __restrict__ list, const unsigned long long* __restrict__ counter) {
     if (p.spd[NB200_SP_SKIP] != 0.0) return;
     __shared__ float wq[NT / 32][7][WQ];
@@ -408,13 +408,15 @@ sparse_solve_kernel(const SparseParams p, const unsigned* __restrict__ list, con
         n_q -= cnt;
         __syncwarp();
     };
-    for (unsigned long long base = ((unsigned long long)blockIdx.x * (NT / 32) + warp) * 32ull; base < n; base += wstride) {
+    const unsigned long long first = ((unsigned long long)blockIdx.x * (NT / 32) + warp) * 32ull + lane;
+    unsigned at_next = first < n ? __ldg(list + first) : 0u;         // list entries are requested one chunk ahead
+    for (unsigned long long base = first - lane; base < n; base += wstride) {
         const unsigned long long i = base + lane;
         bool keep = false;
         float h[6];
-        unsigned at = 0;
+        const unsigned at = at_next;
+        at_next = i + wstride < n ? __ldg(list + i + wstride) : 0u;
         if (i < n) {
-            at = list[i];
             const unsigned zb = at / plane, rem = at - zb * plane;
             const unsigned y = rem / nx, x = rem - y * nx;
             if (div_mode == NB200_DIV_POW2) candidate_hessian<2>(p, (long long)at, (long long)plane, (int)zb, (int)y, (int)x, h);
@@ -496,7 +498,7 @@ extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float*
         sparse_stream_kernel<<<(unsigned)(nbricks < cap_s ? nbricks : cap_s), NT, 0, st>>>(p, list, counter);
         int rc = nb::check_launch("frangi_sparse(stream)");
         if (rc) return rc;
-        sparse_solve_kernel<<<(unsigned)(3 * nb::sm_count()), NT, 0, st>>>(p, list, counter);
+        sparse_solve_kernel<<<(unsigned)(4 * nb::sm_count()), NT, 0, st>>>(p, list, counter);
         return nb::check_launch("frangi_sparse(solve)");
     }
     p.bz = BZ;
