@@ -170,7 +170,13 @@ class FrangiEngine3D:
         self.n_samples = self.n_lat_z * math.ceil(ny / sy) * math.ceil(nx / sx)
         dev = self.device
         f32 = dict(dtype=torch.float32, device=dev)
-        self.gauss = [torch.empty((self.nz_buf, ny, nx), **f32) for _ in range(2)]
+        self.gauss = [torch.empty((self.nz_buf, ny, nx), **f32) for _ in range(3)]   # sigma i, scratch, sigma i+1
+        self.code = torch.empty((self.nz_buf, ny, nx), **f32)                        # K2's per-voxel record
+        self.side_stream = torch.cuda.Stream(dev)
+        # blur of sigma i+1 on a side stream under K2/K3 of sigma i.  Measured: no gain on B200 — K2 holds 61 K of
+        # the 64 K registers of an SM (2 CTAs x 256 threads x 120), so the block scheduler cannot co-schedule the
+        # blur CTAs and the two streams serialise (84.2 vs 84.4 ms/step); kept as an option, off by default
+        self.overlap_blur = False
         self.acc = torch.empty((self.nz_buf, ny, nx), **f32)
         self.out = torch.empty((self.nz_own, ny, nx), **f32)
         self.samples = torch.empty(max(1, self.n_samples), **f32)
@@ -264,74 +270,122 @@ class FrangiEngine3D:
         own.copy_(frame)
         self.cur = 0
 
-    def run_sigmas(self):
-        """filtering.py:814-851 for every sigma; leaves max-over-sigma / dead flags in ``acc``."""
+    def _blur_sigma(self, i, src_idx, last_reader):
+        """F1 for sigma i on the CURRENT stream: incremental blur of ``gauss[src_idx]`` (axes Z, Y, X in scipy's
+        order) into the other volumes; returns the index of the volume holding the result.  ``gauss[src_idx]`` itself
+        is never written (the previous sigma's K2/K3 may still be reading it on another stream); a destination
+        volume is only written after the event of its last reader."""
+        taps = self.steps[i]
+        if not any(t is not None and t[1] > 0 for t in taps):
+            return src_idx
         st = _stream()
-        self.acc.zero_()
+        cur_stream = torch.cuda.current_stream(self.device)
+        rz = taps[0][1] if taps[0] is not None else 0
+        self.exchange_halo(self.gauss[src_idx], rz + 2)
+        # Z pass over owned+2 planes (reads the exchanged halo); Y/X passes likewise so the Hessian stencil finds
+        # blurred neighbours without a second exchange
+        v = self.vol(2, 2)
+        dp = C.POINTER(C.c_double)
+        fuse_yx = (self.fuse_yx and taps[1] is not None and taps[2] is not None
+                   and taps[1][1] == taps[2][1] and 1 <= taps[1][1] <= 8)
+        free = [k for k in range(len(self.gauss)) if k != src_idx]
+        cur, n_pass = src_idx, 0
+        for axis, t in enumerate(taps):
+            if t is None or t[1] == 0:
+                continue
+            w, r = t
+            dst = free[n_pass % 2] if cur == src_idx or cur != free[n_pass % 2] else free[(n_pass + 1) % 2]
+            ev = last_reader.pop(dst, None)
+            if ev is not None:
+                cur_stream.wait_event(ev)
+            if axis == 1 and fuse_yx:
+                self._call("nb200_gauss_yx", _ptr(self.gauss[cur]), _ptr(self.gauss[dst]), C.byref(v), w.ctypes.data_as(dp),
+                           taps[2][0].ctypes.data_as(dp), r, st)
+                cur = dst
+                break
+            self._call("nb200_gauss_axis", _ptr(self.gauss[cur]), _ptr(self.gauss[dst]), C.byref(v), axis,
+                       w.ctypes.data_as(dp), r, st)
+            cur = dst
+            n_pass += 1
+        return cur
+
+    def _analyse_sigma(self, i, g):
+        """F2-F9 for sigma i on the CURRENT stream: gamma, Hessian statistics, Frobenius threshold, K3."""
+        st = _stream()
+        sp_i = self.sp[i]
         sz, sy, sx = self.strides
-        for i, taps in enumerate(self.steps):
-            sp_i = self.sp[i]
-            # F1: incremental blur, axes Z, Y, X in order (scipy processes axes 0,1,2)
-            if any(t is not None for t in taps):
-                rz = taps[0][1] if taps[0] is not None else 0
-                self.exchange_halo(self.gauss[self.cur], rz + 2)
-                # Z pass over owned+2 planes (reads the exchanged halo); Y/X passes likewise so the
-                # Hessian stencil finds blurred neighbours without a second exchange
-                v = self.vol(2, 2)
-                dp = C.POINTER(C.c_double)
-                fuse_yx = (self.fuse_yx and taps[1] is not None and taps[2] is not None
-                           and taps[1][1] == taps[2][1] and 1 <= taps[1][1] <= 8)
-                for axis, t in enumerate(taps):
-                    if t is None or t[1] == 0:
-                        continue
-                    w, r = t
-                    src, dst = self.gauss[self.cur], self.gauss[1 - self.cur]
-                    if axis == 1 and fuse_yx:
-                        self._call("nb200_gauss_yx", _ptr(src), _ptr(dst), C.byref(v), w.ctypes.data_as(dp),
-                                   taps[2][0].ctypes.data_as(dp), r, st)
-                        self.cur = 1 - self.cur
-                        break
-                    self._call("nb200_gauss_axis", _ptr(src), _ptr(dst), C.byref(v), axis, w.ctypes.data_as(dp), r, st)
-                    self.cur = 1 - self.cur
-            g = self.gauss[self.cur]
-            own = self.vol()
-            # F2/F3: gamma from the positive lattice sample of the blurred volume
-            self._call("nb200_lattice_sample", _ptr(g), C.byref(own), sz, sy, sx, _ptr(self.samples), st)
-            self._histogram(self.samples, self.n_samples, _cabi.TF_NONE, None)
-            self._call("nb200_finalize_gamma", _ptr(self.hist), _ptr(sp_i), st)
-            # F4: Hessian statistics (max|H|, max frob^2, frob samples)
-            self._call("nb200_hstats_reset", _ptr(self.hstats), st)
-            # the other ping-pong volume is free between two blurs: K2 leaves its per-voxel record there
-            code = self.gauss[1 - self.cur] if self.sparse_k3 else None
-            self._call("nb200_hessian_stats_code", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
+        own = self.vol()
+        # F2/F3: gamma from the positive lattice sample of the blurred volume
+        self._call("nb200_lattice_sample", _ptr(g), C.byref(own), sz, sy, sx, _ptr(self.samples), st)
+        self._histogram(self.samples, self.n_samples, _cabi.TF_NONE, None)
+        self._call("nb200_finalize_gamma", _ptr(self.hist), _ptr(sp_i), st)
+        # F4: Hessian statistics (max|H|, max frob^2, frob samples) + K2's per-voxel record for the sparse K3
+        self._call("nb200_hstats_reset", _ptr(self.hstats), st)
+        code = self.code if self.sparse_k3 else None
+        self._call("nb200_hessian_stats_code", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
+                   sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), _ptr(code), st)
+        self.reduce_hstats(self.hstats)
+        self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
+        if self.div_mode == _cabi.DIV_FAST:
+            # safety net of the fast division: kernels that return at once unless sp[UNSAFE] was just set
+            self._call("nb200_hessian_stats_redo", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
                        sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), _ptr(code), st)
             self.reduce_hstats(self.hstats)
             self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
-            if self.div_mode == _cabi.DIV_FAST:
-                # safety net of the fast division: kernels that return at once unless sp[UNSAFE] was just set
-                self._call("nb200_hessian_stats_redo", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
-                           sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), _ptr(code), st)
-                self.reduce_hstats(self.hstats)
-                self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
-            # F5: Frobenius threshold
-            fixed = float("nan") if self.p.frob_thresh is None else float(self.p.frob_thresh)
-            division = float(self.p.frob_thresh_division or 0.0)
-            if self.p.frob_thresh is None and division != 0.0:
-                div_ptr = C.c_void_p(sp_i.data_ptr() + 8 * _cabi.SP_MAX_ABS)
-                self._histogram(self.samples, self.n_samples, _cabi.TF_DIV, div_ptr)
-            else:
-                self._call("nb200_hist_reset", _ptr(self.hist), st)
-            self._call("nb200_finalize_frob", _ptr(self.hist), _ptr(self.hstats), fixed, division, _ptr(sp_i), st)
-            # F4-F9 fused
-            if self.sparse_k3:
-                # candidate list: the output volume is idle until finalize() and holds one word per owned voxel
-                lst = self.out if self.sparse_list else None
-                self._call("nb200_frangi_sparse", _ptr(g), _ptr(code), _ptr(self.acc), C.byref(own), self._fd_c,
-                           self.div_mode, float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i),
-                           _ptr(lst), self.out.numel(), _ptr(self.list_count), st)
-            else:
-                self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode,
-                           float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
+        # F5: Frobenius threshold
+        fixed = float("nan") if self.p.frob_thresh is None else float(self.p.frob_thresh)
+        division = float(self.p.frob_thresh_division or 0.0)
+        if self.p.frob_thresh is None and division != 0.0:
+            div_ptr = C.c_void_p(sp_i.data_ptr() + 8 * _cabi.SP_MAX_ABS)
+            self._histogram(self.samples, self.n_samples, _cabi.TF_DIV, div_ptr)
+        else:
+            self._call("nb200_hist_reset", _ptr(self.hist), st)
+        self._call("nb200_finalize_frob", _ptr(self.hist), _ptr(self.hstats), fixed, division, _ptr(sp_i), st)
+        # F4-F9 fused
+        if self.sparse_k3:
+            # candidate list: the output volume is idle until finalize() and holds one word per owned voxel
+            lst = self.out if self.sparse_list else None
+            self._call("nb200_frangi_sparse", _ptr(g), _ptr(code), _ptr(self.acc), C.byref(own), self._fd_c,
+                       self.div_mode, float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i),
+                       _ptr(lst), self.out.numel(), _ptr(self.list_count), st)
+        else:
+            self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode,
+                       float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
+
+    def run_sigmas(self):
+        """filtering.py:814-851 for every sigma; leaves max-over-sigma / dead flags in ``acc``.
+
+        The blur of sigma i+1 only needs the blurred volume of sigma i, so it runs on a side stream while the
+        caller's stream does K2 / thresholds / K3 of sigma i: the bandwidth-bound Z pass and the FP64-bound Y+X
+        pass fill the issue slots and the HBM bandwidth that the issue-bound Hessian march leaves idle.  Three
+        blur volumes rotate (source of truth of sigma i, scratch, result of sigma i+1); CUDA events order the
+        reuse.  Per-sigma results do not depend on the overlap (same kernels, same inputs)."""
+        main = torch.cuda.current_stream(self.device)
+        self.acc.zero_()
+        nsig = len(self.steps)
+        if not self.overlap_blur:
+            src = self.cur
+            for i in range(nsig):
+                src = self._blur_sigma(i, src, {})
+                self._analyse_sigma(i, self.gauss[src])
+            self.cur = src
+            return
+        side = self.side_stream
+        side.wait_stream(main)                       # the frame has been loaded on the caller's stream
+        last_reader = {}
+        src = self.cur
+        for i in range(nsig):
+            with torch.cuda.stream(side):
+                src = self._blur_sigma(i, src, last_reader)
+                ev_blur = torch.cuda.Event()
+                ev_blur.record(side)
+            main.wait_event(ev_blur)
+            self._analyse_sigma(i, self.gauss[src])
+            ev_read = torch.cuda.Event()
+            ev_read.record(main)
+            last_reader[src] = ev_read
+        main.wait_stream(side)
+        self.cur = src
 
     def finalize(self, apply_mask_volume=True, out=None):
         """filtering.py:926 (V*masks) + :1014-1018 / :952-967 (_mask_volume).  ``out``: optional device buffer of

@@ -179,6 +179,10 @@ def test_sparse_k3_equals_dense_march(name):
     assert eng.sparse_k3 and eng.fuse_yx
     a = eng.filter_frame(frame, apply_mask_volume=False).clone()
     acc_a = eng.acc.clone()
+    eng.overlap_blur = True                      # blur of sigma i+1 on a side stream under K2/K3 of sigma i
+    a1 = eng.filter_frame(frame, apply_mask_volume=False).clone()
+    assert torch.equal(a, a1) and torch.equal(acc_a, eng.acc)
+    eng.overlap_blur = False
     eng.sparse_list = False                      # one kernel with shared-memory queues instead of stream + solve
     a2 = eng.filter_frame(frame, apply_mask_volume=False).clone()
     assert torch.equal(a, a2) and torch.equal(acc_a, eng.acc)
