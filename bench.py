@@ -109,7 +109,8 @@ def run_reference_arm(args):
     procs = max(1, (os.cpu_count() or 1))
     steps = max(1, args.steps)
     vals = []
-    for _ in range(args.warmup):
+    warm = min(1, max(0, args.warmup))      # numpy/scipy need no more than one pass to page everything in
+    for _ in range(warm):
         cpu_baseline(args.cpu_size, procs)
     t_all0 = time.perf_counter()
     for _ in range(steps):
@@ -117,13 +118,13 @@ def run_reference_arm(args):
     wall = time.perf_counter() - t_all0
     v = float(np.mean([x["value"] for x in vals]))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "voxels/s", "n_gpus": args.gpus,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
+            "steps": steps, "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 accumulate / eigvalsh)", "data": "synthetic",
             "config": {"workload": f"reference CPU path (oracle port) on {procs} x {args.cpu_size}^3 crops of the "
                                    "1024^3 tubular phantom workload, 6 sigmas", "sigmas": SIGMAS_CFG3},
             "cpu_baseline": dict(vals[-1], value=v),
             "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -260,12 +261,35 @@ def run_b200_arm(args):
                        "l2_policy": "inputs larger than L2 (4 B x voxels per buffer >> 126 MB)", "seed": 3},
             "clocks": clocks, "e2e": e2e, "gpu_launches": timed_launches, "roofline": roofline, "roofline_kernels": roofs, "cpu_baseline": cpu,
             "kernel_ms_per_step": breakdown, "kernel_ms_per_sigma": per_sigma}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything libraries write to fd 1 (e.g. NCCL's version banner) goes to stderr; the ONE JSON line is written to
+    the saved descriptor by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
