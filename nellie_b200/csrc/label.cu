@@ -145,21 +145,21 @@ ccl_merge_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dim
             if (in(0, -1, 0) && !(w_in && in(0, -1, -1))) unite(parent, me, off(0, -1, 0));
             if (in(-1, 0, 0) && !(w_in && in(-1, 0, -1))) unite(parent, me, off(-1, 0, 0));
         } else {
-            // 26-/8-connectivity, backward half.  A set centre neighbour already ties its whole
-            // row / plane together through those voxels' own links, so it stands for the rest.
-            if (in(0, -1, 0)) unite(parent, me, off(0, -1, 0));
-            else {
-                if (in(0, -1, -1)) unite(parent, me, off(0, -1, -1));
-                if (in(0, -1, 1)) unite(parent, me, off(0, -1, 1));
-            }
-            if (z > 0) {
-                if (in(-1, 0, 0)) unite(parent, me, off(-1, 0, 0));
-                else {
+            // 26-/8-connectivity, backward half, ONE union per overlap of two x-runs: my run [a,b] touches every
+            // run of a backward row that meets [a-1, b+1].  Such a run either covers a-1 or a (linked by the first
+            // voxel of my run) or starts at s in [a+1, b+1] (linked by my voxel s-1, which sees the start diagonally).
+            const int dz_lo = z > 0 ? -1 : 0;
+            for (int dz = dz_lo; dz <= 0; ++dz) {
+                const int dy_hi = dz == 0 ? -1 : 1;          // same plane: only the row above
 #pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-                        for (int dx = -1; dx <= 1; ++dx)
-                            if ((dy != 0 || dx != 0) && in(-1, dy, dx)) unite(parent, me, off(-1, dy, dx));
+                for (int dy = -1; dy <= 1; ++dy) {
+                    if (dy > dy_hi) break;
+                    const bool c0 = in(dz, dy, 0);
+                    if (!c0 && in(dz, dy, 1)) unite(parent, me, off(dz, dy, 1));
+                    if (!w_in) {
+                        if (c0) unite(parent, me, off(dz, dy, 0));
+                        else if (in(dz, dy, -1)) unite(parent, me, off(dz, dy, -1));
+                    }
                 }
             }
         }
