@@ -120,54 +120,81 @@ ccl_init_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims
     }
 }
 
+// Unions are found in lock step (every lane tests the same neighbour relation of its own voxel) but carried out
+// through a per-warp shared-memory queue of (a, b) pairs: 32 pairs are united at a time, one per lane, so the
+// pointer-chasing find / atomicMin loops run with full warps instead of the one or two lanes per instruction
+// that a voxel-by-voxel unite() leaves active (measured: 1.2-1.7 active threads per instruction, 9-16 ms per merge
+// of a 512^3 frame).
 template <bool FULL_CONN, bool BORDER_OUTSIDE>
 __global__ void __launch_bounds__(THREADS)
 ccl_merge_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims d, int* __restrict__ parent) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
-         i += (long long)gridDim.x * blockDim.x) {
-        if (mask[i] != want) continue;
-        const int z = (int)(i / d.plane);
-        const long long rem = i - (long long)z * d.plane;
-        const int y = (int)(rem / d.nx), x = (int)(rem - (long long)y * d.nx);
+    __shared__ int2 queue[THREADS / 32][64];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int2* q = queue[threadIdx.x >> 5];
+    int n_q = 0;                                          // warp-uniform
+    auto push = [&](bool has, int a, int b) {            // called by all lanes of the warp
+        const unsigned bits = __ballot_sync(0xffffffffu, has);
+        if (bits == 0u) return;
+        if (has) q[n_q + __popc(bits & lt)] = make_int2(a, b);
+        n_q += __popc(bits);
+        if (n_q >= 32) {
+            __syncwarp();
+            const int2 pr = q[n_q - 32 + lane];
+            n_q -= 32;
+            unite(parent, pr.x, pr.y);
+            __syncwarp();
+        }
+    };
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long base = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); base < d.total; base += stride) {
+        const long long i = base + lane;
+        const bool valid = i < d.total && mask[i] == want;
+        int z = 0, y = 0, x = 0;
+        if (valid) {
+            z = (int)(i / d.plane);
+            const long long rem = i - (long long)z * d.plane;
+            y = (int)(rem / d.nx);
+            x = (int)(rem - (long long)y * d.nx);
+        }
         const int me = (int)i;
         auto in = [&](int dz, int dy, int dx) -> bool {
             const int zz = z + dz, yy = y + dy, xx = x + dx;
-            if (zz < 0 || yy < 0 || yy >= d.ny || xx < 0 || xx >= d.nx) return false;
+            if (!valid || zz < 0 || yy < 0 || yy >= d.ny || xx < 0 || xx >= d.nx) return false;
             return mask[i + (long long)dz * d.plane + (long long)dy * d.nx + dx] == want;
         };
         auto off = [&](int dz, int dy, int dx) -> int {
             return (int)(i + (long long)dz * d.plane + (long long)dy * d.nx + dx);
         };
         const bool w_in = in(0, 0, -1);
-        if (w_in && (x & 31) == 0) unite(parent, me, me - 1);      // stitch 32-wide windows of one run
+        push(w_in && (x & 31) == 0, me, me - 1);               // stitch 32-wide windows of one run
         if (!FULL_CONN) {
             // 6-/4-connectivity: link to the row above / plane above once per overlap of two runs
-            if (in(0, -1, 0) && !(w_in && in(0, -1, -1))) unite(parent, me, off(0, -1, 0));
-            if (in(-1, 0, 0) && !(w_in && in(-1, 0, -1))) unite(parent, me, off(-1, 0, 0));
+            push(in(0, -1, 0) && !(w_in && in(0, -1, -1)), me, off(0, -1, 0));
+            push(in(-1, 0, 0) && !(w_in && in(-1, 0, -1)), me, off(-1, 0, 0));
         } else {
             // 26-/8-connectivity, backward half, ONE union per overlap of two x-runs: my run [a,b] touches every
             // run of a backward row that meets [a-1, b+1].  Such a run either covers a-1 or a (linked by the first
             // voxel of my run) or starts at s in [a+1, b+1] (linked by my voxel s-1, which sees the start diagonally).
-            const int dz_lo = z > 0 ? -1 : 0;
-            for (int dz = dz_lo; dz <= 0; ++dz) {
-                const int dy_hi = dz == 0 ? -1 : 1;          // same plane: only the row above
+#pragma unroll
+            for (int dz = -1; dz <= 0; ++dz) {
 #pragma unroll
                 for (int dy = -1; dy <= 1; ++dy) {
-                    if (dy > dy_hi) break;
+                    if (dz == 0 && dy >= 0) continue;          // same plane: only the row above
                     const bool c0 = in(dz, dy, 0);
-                    if (!c0 && in(dz, dy, 1)) unite(parent, me, off(dz, dy, 1));
-                    if (!w_in) {
-                        if (c0) unite(parent, me, off(dz, dy, 0));
-                        else if (in(dz, dy, -1)) unite(parent, me, off(dz, dy, -1));
-                    }
+                    const bool cp = in(dz, dy, 1), cm = in(dz, dy, -1);
+                    push(valid && !c0 && cp, me, off(dz, dy, 1));
+                    push(valid && !w_in && (c0 || cm), me, c0 ? off(dz, dy, 0) : off(dz, dy, -1));
                 }
             }
         }
         if (BORDER_OUTSIDE) {
             const bool edge = z == 0 || z == d.nz - 1 || y == 0 || y == d.ny - 1 || x == 0 || x == d.nx - 1;
-            if (edge) link_outside(parent, me);
+            push(valid && edge, me, OUTSIDE);
         }
     }
+    __syncwarp();
+    if (lane < n_q) unite(parent, q[lane].x, q[lane].y);
 }
 
 __global__ void __launch_bounds__(THREADS)
