@@ -238,7 +238,9 @@ def run_b200_arm(args):
            "nb200_frangi_accumulate": (12.0, "K3 march_kernel<FrangiEpi> (dense form)"),
            "nb200_finalize_opening": (8.0, "K5 opening_march: percentile mask + binary opening (R 4 + W 4)")}
     # DRAM bytes per launch from the ncu --set full captures under profiles/ (1024^3, one GPU): read + write
-    TRAFFIC_1024 = {"nb200_gauss_axis": 8.62e9, "nb200_gauss_yx": 8.55e9, "nb200_hessian_stats_code": 8.74e9}
+    # (profiles/r1e_ncu_full_1024.md; K3 = stream + solve of the sigma-1.4 launch, the sigma-1.0 launch moves 36.7e9)
+    TRAFFIC_1024 = {"nb200_gauss_axis": 8.62e9, "nb200_gauss_yx": 8.55e9, "nb200_hessian_stats_code": 8.75e9,
+                    "nb200_frangi_sparse": 17.6e9, "nb200_finalize_opening": 9.32e9}
     roofs = {}
     for name, (bpv, label) in ALG.items():
         cnt, tot = prof.get(name, (0, 0.0))
