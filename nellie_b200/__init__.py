@@ -1,12 +1,10 @@
 """nellie_b200 — B200-native (sm_100a) implementation of nellie's Filter + Label hot path.
 
-Public surface mirrors ``nellie.segmentation``: :class:`Filter`, :class:`Label`.
+Public surface mirrors ``nellie.segmentation``: :class:`Filter`, :class:`Label`; ``imio`` is the minimal OME-TIFF
+layer under them (``StackInfo`` = the ``ImInfo`` attributes and methods the two stages use) and
+``pipeline.FramePipeline`` the double-buffered H2D / compute / D2H frame stream behind ``Filter.run``.
 """
 from .filtering import Filter  # noqa: F401
-
-try:  # Label arrives with label.cu
-    from .labelling import Label  # noqa: F401
-except ImportError:  # pragma: no cover
-    pass
+from .labelling import Label  # noqa: F401
 
 __all__ = ["Filter", "Label"]
