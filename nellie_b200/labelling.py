@@ -276,15 +276,43 @@ class Label:
             return eng.label(frangi, ft, rawf, it), ft
 
     # ---- top level (reference: labelling.py:697-778) -------------------------------------------------
+    def _stage(self, view, slot):
+        """Host frame (memmap slice / ndarray) -> device float32 through a persistent pinned buffer (one per slot)."""
+        arr = np.asarray(view)
+        if not arr.dtype.isnative:
+            arr = arr.astype(arr.dtype.newbyteorder("="))
+        if arr.dtype in (np.uint32, np.uint64, np.float64):
+            arr = arr.astype(np.float32)          # xp.asarray(frame, dtype=float32) rounds once; same value here
+        src = torch.from_numpy(np.ascontiguousarray(arr))
+        bufs = self.__dict__.setdefault("_pinned", {})
+        buf = bufs.get(slot)
+        if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
+            buf = bufs[slot] = torch.empty(src.shape, dtype=src.dtype).pin_memory()
+        buf.copy_(src)
+        t = buf.to(self._torch_device(), non_blocking=True)
+        return t if t.dtype == torch.float32 else t.to(torch.float32)
+
     def _run_segmentation(self):
+        """T loop of labelling.py:697-734: every frame is uploaded once (the thresholds and the labelling share the
+        device copies), labelled on the device, downloaded through a pinned buffer and written to the memmap."""
+        need_raw = bool(self.otsu_thresh_intensity) or self.threshold is not None
         for t in range(self.num_t):
             if self.viewer is not None:
                 self.viewer.status = f"Extracting organelles. Frame: {t + 1} of {self.num_t}."
             original_view = self.im_memmap[t, ...]
             frangi_view = self.frangi_memmap[t, ...]
-            it, ft = self._compute_frame_thresholds(original_view, frangi_view)
-            labels = self._run_frame_full_volume(t, original_view, frangi_view, it, ft)
-            self.instance_label_memmap[t, ...] = labels
+            logger.info("Running semantic segmentation, volume %s/%s", t, (self.num_t or 1) - 1)
+            eng = self._engine_for(frangi_view.shape)
+            with torch.cuda.device(eng.device):
+                frangi = self._stage(frangi_view, "frangi")
+                raw = self._stage(original_view, "raw") if need_raw else None
+                labels, _ = self.label_frame_device(frangi, raw)      # host syncs inside (threshold scalars)
+                bufs = self.__dict__.setdefault("_pinned", {})
+                host = bufs.get("labels")
+                if host is None or host.shape != labels.shape:
+                    host = bufs["labels"] = torch.empty(labels.shape, dtype=torch.int32).pin_memory()
+                host.copy_(labels)
+            self.instance_label_memmap[t, ...] = host.numpy()
             if (t + 1) % self.flush_interval == 0 and hasattr(self.instance_label_memmap, "flush"):
                 self.instance_label_memmap.flush()
         if hasattr(self.instance_label_memmap, "flush"):
