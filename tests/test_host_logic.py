@@ -175,3 +175,31 @@ def test_vesselness_matches_oracle_bitwise(hostmath):
     out = np.empty(len(ev2), np.float32)
     hostmath.hm_vesselness2(_vp(ev2), _vp(out), C.c_long(len(ev2)), C.c_float(0.5), C.c_float(77.0))
     assert np.array_equal(out, ref)
+
+
+def test_provably_zero_tests_never_reject_a_nonzero_response(hostmath):
+    """K2 flags a voxel / K3 drops a candidate only when the reference's response is exactly zero: eigenvalues from
+    numpy's eigvalsh (f64), rounded to f32, sorted by magnitude, zeroed when l2 > 0 or l3 > 0 (filtering.py:759-761).
+    Random matrices at many scales, tube-like and plate-like spectra, and matrices sitting right at the margins."""
+    rng = np.random.default_rng(7)
+    n = 200_000
+    cases = []
+    for scale in (1e-6, 1.0, 3e3, 1e8):
+        cases.append(rng.standard_normal((n, 6)).astype(np.float32) * np.float32(scale))
+    # rotated diagonal spectra: two negative + one small eigenvalue of either sign (tubes), near-degenerate ones
+    lam = np.stack([rng.uniform(-1, 0, n), rng.uniform(-1, 0, n), rng.normal(0, 1e-4, n)], 1)
+    lam2 = np.stack([rng.normal(0, 1e-5, n), rng.normal(0, 1e-5, n), rng.uniform(-1, 1, n)], 1)
+    for L in (lam, lam2, lam * 1e4):
+        q, _ = np.linalg.qr(rng.standard_normal((n, 3, 3)))
+        H = np.einsum("nij,nj,nkj->nik", q, L, q)
+        cases.append(np.stack([H[:, 0, 0], H[:, 0, 1], H[:, 0, 2], H[:, 1, 1], H[:, 1, 2], H[:, 2, 2]], 1).astype(np.float32))
+    h6 = np.ascontiguousarray(np.concatenate(cases))
+    out = np.empty(len(h6), np.uint8)
+    hostmath.hm_zero_tests(_vp(h6), _vp(out), C.c_long(len(h6)))
+    ev = _eig_ref(h6)                                   # float32 eigenvalues sorted by |.|
+    nonzero = ~((ev[:, 2] > 0) | (ev[:, 1] > 0))        # the reference keeps a response only for these
+    flagged = out != 0
+    assert flagged.any() and (~flagged).any()
+    assert not (flagged & nonzero).any(), int((flagged & nonzero).sum())
+    # the tests are worth having: most matrices with a zero response are caught without an eigen-solve
+    assert (flagged & ~nonzero).sum() > 0.8 * (~nonzero).sum()
