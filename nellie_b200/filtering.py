@@ -39,7 +39,7 @@ class Filter:
                  max_radius_um: float = 1.0, alpha_sq: float = 0.5, beta_sq: float = 0.5, frob_thresh=None,
                  frob_thresh_division=2, viewer=None, device: str = "auto", low_memory: bool = False,
                  max_chunk_voxels: int = int(1e6), max_threshold_samples: int = int(1e6), sigmas=None,
-                 cuda_device=None):
+                 cuda_device=None, t_shard=None):
         dev = (device or "auto").lower()
         if dev == "cpu":
             raise ValueError("nellie_b200.Filter implements the CUDA path only; device='cpu' belongs to "
@@ -79,6 +79,9 @@ class Filter:
         self.halo = None
         self._explicit_sigmas = None if sigmas is None else [float(s) for s in sigmas]
         self._cuda_device = cuda_device
+        # T-sharding: (rank, world) -> this object handles frames t with t % world == rank; frames are
+        # independent (per-frame gamma / thresholds, filtering.py:1007-1012), so ranks share nothing but the output file
+        self.t_shard = None if t_shard is None else (int(t_shard[0]), int(t_shard[1]))
         self._engine = None
         self._engine_key = None
         _cabi.load()  # fail at construction when the CUDA library is absent
@@ -219,9 +222,12 @@ class Filter:
             if hasattr(self.frangi_memmap, "flush"):
                 self.frangi_memmap.flush()
 
+        from .sharding import frames_of_rank
+        frames = list(range(self.num_t)) if self.t_shard is None else frames_of_rank(self.num_t, *self.t_shard)
         with torch.cuda.device(eng.device):
-            FramePipeline(eng).run(self.num_t, get_in, get_out, apply_mask_volume=True, on_frame=on_frame,
-                                   after_store=after_store)
+            FramePipeline(eng).run(len(frames), lambda k: get_in(frames[k]), lambda k: get_out(frames[k]),
+                                   apply_mask_volume=True, on_frame=lambda k: on_frame(frames[k]),
+                                   after_store=lambda k: after_store(frames[k]))
 
     def run(self, mask=True):
         logger.info("Running Frangi filter (nellie_b200).")

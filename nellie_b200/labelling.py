@@ -131,7 +131,7 @@ class Label:
     def __init__(self, im_info, num_t=None, threshold=None, otsu_thresh_intensity=False, viewer=None,
                  chunk_z=None, flush_interval=1, min_radius_um=0.25, threshold_sampling_pixels=1_000_000,
                  histogram_nbins=256, device="auto", low_memory: bool = False, max_chunk_voxels: int = int(1e6),
-                 cuda_device=None):
+                 cuda_device=None, t_shard=None):
         dev = (device or "auto").lower()
         if dev == "cpu":
             raise ValueError("nellie_b200.Label implements the CUDA path only; device='cpu' belongs to "
@@ -165,6 +165,8 @@ class Label:
         self.ndim = 2 if im_info.no_z else 3
         self.min_area_pixels = self._compute_min_area_pixels()
         self._cuda_device = cuda_device
+        # T-sharding: (rank, world) -> frames t with t % world == rank (label ids restart per frame, labelling.py:701-706)
+        self.t_shard = None if t_shard is None else (int(t_shard[0]), int(t_shard[1]))
         self._engine = None
         _cabi.load()
 
@@ -296,7 +298,9 @@ class Label:
         """T loop of labelling.py:697-734: every frame is uploaded once (the thresholds and the labelling share the
         device copies), labelled on the device, downloaded through a pinned buffer and written to the memmap."""
         need_raw = bool(self.otsu_thresh_intensity) or self.threshold is not None
-        for t in range(self.num_t):
+        from .sharding import frames_of_rank
+        frames = range(self.num_t) if self.t_shard is None else frames_of_rank(self.num_t, *self.t_shard)
+        for t in frames:
             if self.viewer is not None:
                 self.viewer.status = f"Extracting organelles. Frame: {t + 1} of {self.num_t}."
             original_view = self.im_memmap[t, ...]

@@ -291,3 +291,37 @@ def test_2d_cuda_graph_replay_equals_eager_launches():
     for t in range(5):
         assert torch.equal(got[t], want[t]), t
     assert any(bool((w > 0).any()) for w in want)
+
+
+def test_t_sharded_runs_fill_the_same_output(tmp_path):
+    """T-sharding: two stage objects with t_shard=(0,2) / (1,2) — what two ranks would run — write
+    disjoint frames of the same files; together they equal the unsharded run."""
+    from nellie_b200 import Filter, Label, imio
+    from nellie_b200.phantoms import tubular_phantom_np
+    dim_res = {"X": 0.1, "Y": 0.1, "Z": 0.2, "T": 1.0}
+    frames = np.stack([tubular_phantom_np((16, 40, 64), seed=900 + t, n_tubes=4) for t in range(5)])
+    full = imio.StackInfo.from_array(frames, "TZYX", dim_res, str(tmp_path / "full"), "p")
+    Filter(full, device="b200").run()
+    Label(full, device="b200").run()
+    shard = imio.StackInfo.from_array(frames, "TZYX", dim_res, str(tmp_path / "shard"), "p")
+    f0 = Filter(shard, device="b200", t_shard=(0, 2))
+    f0.run()                                                   # allocates the output file and fills frames 0, 2, 4
+    pre = imio.memmap_ome_tiff(shard.pipeline_paths["im_preprocessed"], "r")
+    assert pre[0].any() and not pre[1].any() and pre[2].any()
+    f1 = Filter(shard, device="b200", t_shard=(1, 2))
+    f1._get_t(); f1._set_default_sigmas()
+    f1.im_memmap = shard.get_memmap(shard.im_path)
+    f1.frangi_memmap = shard.get_memmap(shard.pipeline_paths["im_preprocessed"])   # rank > 0 opens, does not re-create
+    f1._run_filter()
+    assert np.array_equal(imio.read_tiff(shard.pipeline_paths["im_preprocessed"]),
+                          imio.read_tiff(full.pipeline_paths["im_preprocessed"]))
+    l0 = Label(shard, device="b200", t_shard=(0, 2))
+    l0.run()
+    l1 = Label(shard, device="b200", t_shard=(1, 2))
+    l1._get_t()
+    l1.im_memmap = shard.get_memmap(shard.im_path)
+    l1.frangi_memmap = shard.get_memmap(shard.pipeline_paths["im_preprocessed"])
+    l1.instance_label_memmap = shard.get_memmap(shard.pipeline_paths["im_instance_label"])
+    l1._run_segmentation()
+    assert np.array_equal(imio.read_tiff(shard.pipeline_paths["im_instance_label"]),
+                          imio.read_tiff(full.pipeline_paths["im_instance_label"]))
