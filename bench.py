@@ -102,11 +102,35 @@ def cpu_baseline(size=112, procs=1):
                       f"{wall:.1f} s wall"}
 
 
+def _host_procs(size):
+    """All host cores, bounded by memory: one oracle process peaks at ~1.8 GB for a 192^3 crop (measured), scaling
+    with the crop volume; never plan for more than half of what the host / cgroup has available."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    need = 1.8e9 * (size / 192.0) ** 3 * 1.3
+    avail = None
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                avail = float(line.split()[1]) * 1024.0
+    except OSError:
+        pass
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v.isdigit():
+                avail = min(avail, float(v)) if avail else float(v)
+        except OSError:
+            pass
+    if avail:
+        cores = min(cores, max(1, int(0.5 * avail / need)))
+    return max(1, cores)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    procs = max(1, (os.cpu_count() or 1))
+    procs = _host_procs(args.cpu_size)
     steps = max(1, args.steps)
     vals = []
     warm = min(1, max(0, args.warmup))      # numpy/scipy need no more than one pass to page everything in
