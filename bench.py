@@ -323,9 +323,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=1024, help="edge of the cubic volume (1024 = BASELINE config #3)")
     ap.add_argument("--tubes", type=int, default=None)
-    ap.add_argument("--cpu-size", type=int, default=192, help="edge of the crop the CPU baseline runs")
+    ap.add_argument("--cpu-size", type=int, default=None,
+                    help="edge of the crop the CPU arms run (default: 192 for the cpu_baseline sample; the reference arm "
+                         "shrinks it so that steps+warmup passes end within ~3 minutes)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.cpu_size is None:
+        args.cpu_size = 192
+        if args.impl == "reference":
+            # one 192^3 crop takes ~40 s per pass (all cores busy with one crop each); keep the whole run near 3 minutes
+            budget = 180.0 / (max(1, args.steps) + min(1, max(0, args.warmup)))
+            args.cpu_size = int(min(192, max(96, 16 * round(192.0 * (budget / 40.0) ** (1.0 / 3.0) / 16))))
     if args.impl == "reference":
         run_reference_arm(args)
     else:
