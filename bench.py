@@ -84,18 +84,40 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, int(raw.size), float(out.max())
 
 
-def cpu_baseline(size=112, procs=1):
+def _cpu_warm(_):
+    from nellie_b200.phantoms import tubular_phantom_np  # noqa: F401  (imports paid before the clock starts)
+    from oracle import pipeline  # noqa: F401
+    return os.getpid()
+
+
+def cpu_baseline(size=112, procs=1, pool=None):
     """Time the oracle on `procs` independent size^3 crops of the workload (one process per crop: the
-    reference path is single-threaded, frames/crops are its only parallel axis)."""
+    reference path is single-threaded, frames/crops are its only parallel axis).  Process start-up and imports
+    are outside the timed region (`pool` = a warmed multiprocessing pool)."""
     if procs == 1:
-        res = [_cpu_worker((size, 1000))]
+        try:                                   # `cores: 1` must be true: keep BLAS/OpenMP pools at one thread
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=1):
+                res = [_cpu_worker((size, 1000))]
+        except ImportError:
+            res = [_cpu_worker((size, 1000))]
         wall = res[0][0]
     else:
-        import multiprocessing as mp
-        with mp.get_context("spawn").Pool(procs) as pool:
+        own = pool is None
+        if own:
+            for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+                os.environ[var] = "1"
+            import multiprocessing as mp
+            pool = mp.get_context("spawn").Pool(procs)
+            pool.map(_cpu_warm, range(procs))
+        try:
             t0 = time.perf_counter()
-            res = pool.map(_cpu_worker, [(size, 1000 + i) for i in range(procs)])
+            res = pool.map(_cpu_worker, [(size, 1000 + i) for i in range(procs)], chunksize=1)
             wall = time.perf_counter() - t0
+        finally:
+            if own:
+                pool.close()
+                pool.join()
     vox = sum(r[1] for r in res)
     return {"value": vox / wall, "unit": "voxels/s", "cores": procs, "kind": "port",
             "sample": f"{procs} x {size}^3 crop(s) of the tubular phantom, 6 sigmas, oracle.pipeline.filter_frame, "
@@ -131,15 +153,29 @@ def run_reference_arm(args):
     if rank != 0:
         return
     procs = _host_procs(args.cpu_size)
+    # one single-threaded oracle process per core: without this every process starts a BLAS/OpenMP pool as wide as the
+    # machine and the oversubscription costs the reference arm 8x (measured)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[var] = "1"
     steps = max(1, args.steps)
     vals = []
     warm = min(1, max(0, args.warmup))      # numpy/scipy need no more than one pass to page everything in
-    for _ in range(warm):
-        cpu_baseline(args.cpu_size, procs)
-    t_all0 = time.perf_counter()
-    for _ in range(steps):
-        vals.append(cpu_baseline(args.cpu_size, procs))
-    wall = time.perf_counter() - t_all0
+    pool = None
+    if procs > 1:
+        import multiprocessing as mp
+        pool = mp.get_context("spawn").Pool(procs)
+        pool.map(_cpu_warm, range(procs))   # interpreter start-up and imports are not the reference's work
+    try:
+        for _ in range(warm):
+            cpu_baseline(args.cpu_size, procs, pool)
+        t_all0 = time.perf_counter()
+        for _ in range(steps):
+            vals.append(cpu_baseline(args.cpu_size, procs, pool))
+        wall = time.perf_counter() - t_all0
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
     v = float(np.mean([x["value"] for x in vals]))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "voxels/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
