@@ -102,13 +102,15 @@ class FramePipeline:
                 if src.is_pinned():
                     return src
                 k = t % depth
-                self.ev_h2d[k].synchronize()
-                buf = self._pin_in(k, src.dtype)
+                with torch.cuda.device(self.dev):      # worker threads start on device 0: pin against OUR device
+                    self.ev_h2d[k].synchronize()
+                    buf = self._pin_in(k, src.dtype)
                 buf.copy_(src)
                 return buf
 
             def store(t, k, dst):
-                self.ev_d2h[k].synchronize()
+                with torch.cuda.device(self.dev):
+                    self.ev_d2h[k].synchronize()
                 out_t = _as_tensor(dst) if not isinstance(dst, torch.Tensor) else dst
                 out_t.copy_(self.pin_out[k])
                 if after_store is not None:
