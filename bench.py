@@ -128,7 +128,7 @@ def _host_procs(size):
     """All host cores, bounded by memory: one oracle process peaks at ~1.8 GB for a 192^3 crop (measured), scaling
     with the crop volume; never plan for more than half of what the host / cgroup has available."""
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    need = 1.8e9 * (size / 192.0) ** 3 * 1.3
+    need = 1.8e9 * (size / 192.0) ** 3 * 1.3 + 0.6e9        # + the interpreter with numpy / scipy / torch loaded
     avail = None
     try:
         for line in open("/proc/meminfo"):
@@ -145,7 +145,7 @@ def _host_procs(size):
             pass
     if avail:
         cores = min(cores, max(1, int(0.5 * avail / need)))
-    return max(1, cores)
+    return max(1, min(cores, 128))
 
 
 def run_reference_arm(args):
