@@ -143,3 +143,28 @@ def test_label_frame_matches_oracle_random_blobs(seed):
     ref2 = P.label_frame(field, spec, 0.5, raw=raw, intensity_thresh=0.3)
     got2 = lab._run_frame_full_volume(0, raw, field, 0.3, 0.5)
     assert np.array_equal(got2, ref2)
+
+
+def test_sharded_labeller_on_one_gpu_equals_the_reference_labels(tmp_path):
+    """nellie_b200/sharded_label.py with the CUDA local-CCL callback (world size 1: no seam, but the whole
+    fill-holes / size filter / majority / numbering chain on device tensors) against the executed reference."""
+    import torch
+    import torch.distributed as dist
+    from nellie_b200.sharded_label import ZShardedLabeller, cuda_local_label
+    g = load_golden("label3d")
+    created = False
+    if not dist.is_initialized():
+        store = dist.FileStore(str(tmp_path / "store"), 1)
+        dist.init_process_group("nccl", store=store, rank=0, world_size=1)
+        created = True
+    try:
+        thr = np.float32(g["meta"]["frangi_thresh"])
+        mask = torch.from_numpy(g["frangi"] > thr).cuda()
+        nz, ny, nx = mask.shape
+        lab = ZShardedLabeller(0, nz, nz, ny, nx, cuda_local_label)
+        got = lab.label(mask, int(g["min_area"])).cpu().numpy()
+        assert got.dtype == np.int32
+        assert np.array_equal(got, g["labels"])
+    finally:
+        if created:
+            dist.destroy_process_group()

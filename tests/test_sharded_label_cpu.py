@@ -1,0 +1,101 @@
+"""Z-sharded Label (nellie_b200/sharded_label.py) on CPU with gloo: seam merge, fill-holes, size filter, majority and
+global numbering against scipy.ndimage on the whole frame (labelling.py:467-509).  scipy stands in for the local CCL
+kernel; everything else is the product's distributed logic."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import scipy.ndimage as ndi
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _scipy_local_label(mask, full_conn):
+    m = mask.cpu().numpy().astype(bool)
+    lab, n = ndi.label(m, structure=np.ones((3, 3, 3), bool) if full_conn else None)
+    return torch.from_numpy(lab.astype(np.int32)), int(n)
+
+
+def _reference_labels(mask, min_area):
+    """labelling.py:467-509 on the whole frame."""
+    structure = np.ones((3, 3, 3), bool)
+    m = ndi.binary_fill_holes(mask)
+    lab, _ = ndi.label(m, structure=structure)
+    areas = np.bincount(lab.ravel())
+    areas[0] = 0
+    keep = (areas >= min_area)[lab]
+    smooth = ndi.uniform_filter(keep.astype(np.float32), size=3) > 0.5
+    out, _ = ndi.label(smooth, structure=structure)
+    return out.astype(np.int32)
+
+
+def _frame(seed, shape, kind):
+    rng = np.random.default_rng(seed)
+    if kind == "blobs":
+        f = ndi.uniform_filter(rng.random(shape).astype(np.float32), 3)
+        return f > np.quantile(f, 0.72)
+    if kind == "shells":          # hollow boxes: holes to fill, some straddling the seams, some open to the border
+        m = np.zeros(shape, bool)
+        nz, ny, nx = shape
+        for z, y, x, h in [(1, 2, 2, 7), (nz // 2 - 3, 10, 4, 6), (nz - 7, 3, 12, 6), (nz // 3, 12, 12, 5), (0, 0, 14, 5)]:
+            m[z:z + h, y:y + h, x:x + h] = True
+            m[z + 1:z + h - 1, y + 1:y + h - 1, x + 1:x + h - 1] = False
+        m[nz // 2, 11, 5] = False  # a pin hole opens one shell along... (still closed: wall is one voxel thick elsewhere)
+        m |= rng.random(shape) < 0.02
+        return m
+    # diagonal staircases: components that only connect through 26-neighbours across seams
+    m = np.zeros(shape, bool)
+    for z in range(shape[0]):
+        m[z, (z * 2) % shape[1], (z * 3) % shape[2]] = True
+        m[z, (z * 2 + 1) % shape[1], (z * 3 + 1) % shape[2]] = True
+        m[z, shape[1] - 1 - (z % shape[1]), z % shape[2]] = True
+    return m
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nellie_b200.sharded_label import ZShardedLabeller
+        from nellie_b200.sharding import z_partition
+        cases = [(1, (23, 20, 24), "blobs", 6), (2, (24, 19, 21), "shells", 1), (3, (17, 9, 11), "stairs", 1),
+                 (4, (31, 16, 18), "blobs", 40)]
+        for seed, shape, kind, min_area in cases:
+            mask = _frame(seed, shape, kind)
+            want = _reference_labels(mask, min_area)
+            z0, z1 = z_partition(shape[0], world)[rank]
+            lab = ZShardedLabeller(z0, z1 - z0, shape[0], shape[1], shape[2], _scipy_local_label)
+            got = lab.label(torch.from_numpy(mask[z0:z1]), min_area).numpy()
+            assert got.dtype == np.int32
+            assert np.array_equal(got, want[z0:z1]), (kind, rank, int((got != want[z0:z1]).sum()))
+            if rank == 0 and kind != "stairs":
+                assert want.max() >= 1, kind
+            # the seam-merge primitive alone: canonical ids ranked = scipy.ndimage.label of the whole mask
+            for full in (True, False):
+                ref, _ = ndi.label(mask, structure=np.ones((3, 3, 3), bool) if full else None)
+                canon = lab.components(torch.from_numpy(mask[z0:z1]), full)
+                ids = torch.unique(canon[canon > 0])
+                from nellie_b200.sharded_label import _all_gather_ragged
+                all_ids = torch.unique(_all_gather_ragged(ids))
+                ranked = torch.where(canon > 0, torch.searchsorted(all_ids, canon.reshape(-1)).reshape(canon.shape) + 1,
+                                     torch.zeros_like(canon)).numpy()
+                assert np.array_equal(ranked, ref[z0:z1]), (kind, full, rank)
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_label_matches_scipy_on_the_whole_frame(world, tmp_path):
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
