@@ -203,3 +203,22 @@ def test_provably_zero_tests_never_reject_a_nonzero_response(hostmath):
     assert not (flagged & nonzero).any(), int((flagged & nonzero).sum())
     # the tests are worth having: most matrices with a zero response are caught without an eigen-solve
     assert (flagged & ~nonzero).sum() > 0.8 * (~nonzero).sum()
+
+
+def test_library_sass_uses_tma_and_packed_f32():
+    """Static guard (no GPU): the built sm_100a library must still contain the TMA plane loads of the Hessian march
+    (UTMALDG.3D + mbarrier transactions), the packed float32x2 arithmetic, and a blur without DFMA contraction."""
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    from nellie_b200 import build
+    if not (os.path.exists(cuobjdump) and os.path.exists(build.LIB)):
+        pytest.skip("cuobjdump or the built library is missing")
+    sass = subprocess.run([cuobjdump, "-sass", build.LIB], capture_output=True, text=True).stdout
+    assert "UTMALDG.3D" in sass and "SYNCS.ARRIVE.TRANS64" in sass
+    assert "FFMA2" in sass and "FMUL2" in sass
+    # per-function check of the blur kernels: DADD / DMUL only
+    blocks = sass.split("Function : ")
+    gauss = [b for b in blocks if b.startswith("_ZN") and ("gauss_z_vec" in b.split("\n")[0] or "gauss_yx_tile" in b.split("\n")[0])]
+    assert gauss, "blur kernels not found in the library"
+    for b in gauss:
+        assert "DADD" in b and "DMUL" in b and "DFMA" not in b, b.split("\n")[0]
