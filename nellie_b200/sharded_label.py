@@ -95,6 +95,43 @@ def _remap(vol: torch.Tensor, old: torch.Tensor, new: torch.Tensor) -> torch.Ten
     return torch.where(hit, new[pos], flat).reshape(vol.shape)
 
 
+def sharded_sample_nonzero(slab: torch.Tensor, z0: int, nz_glob: int, sampling_pixels: int,
+                           gate: Optional[torch.Tensor] = None, gate_thresh: Optional[float] = None, group=None) -> torch.Tensor:
+    """``Label._sample_nonzero`` (labelling.py:385-438) of a Z-sharded frame: ``flat[off::step]`` of the GLOBAL
+    flattened frame, ``step = size // sampling_pixels``, offsets 0 then ``step // 2``, keeping positive values (and
+    ``gate > gate_thresh``); full scan when both offsets come up empty.  Every rank takes the lattice points that fall
+    into its slab; the kept values are all-gathered in rank order, so every rank holds the same sample, in the same
+    order as the single-GPU path, and derives the same thresholds from it."""
+    nz, ny, nx = (int(v) for v in slab.shape)
+    plane = ny * nx
+    size = int(nz_glob) * plane
+    step = max(size // max(1, int(sampling_pixels)), 1)
+    offsets = (0, step // 2) if step > 1 and step // 2 > 0 else (0,)
+    flat = slab.reshape(-1)
+    gflat = gate.reshape(-1) if (gate is not None and gate_thresh is not None) else None
+    g0 = int(z0) * plane                                 # global flat index of my first voxel
+
+    def gather(vals):
+        bits = vals.contiguous().view(torch.int32).to(torch.int64)        # ragged all-gather works on int64
+        return _all_gather_ragged(bits, group).to(torch.int32).view(torch.float32)
+
+    for off in offsets:
+        first = (off - g0) % step                        # first local index with (g0 + i - off) % step == 0, i >= 0
+        if g0 + first < off:
+            first += ((off - g0 - first) + step - 1) // step * step
+        vals = flat[first::step]
+        keep = vals > 0
+        if gflat is not None:
+            keep &= gflat[first::step] > gate_thresh
+        allv = gather(vals[keep])
+        if allv.numel() > 0 or step == 1:
+            return allv
+    keep = flat > 0
+    if gflat is not None:
+        keep &= gflat > gate_thresh
+    return gather(flat[keep])
+
+
 class ZShardedLabeller:
     """Distributed ``_get_labels`` for the slab ``[z0, z0 + nz_own)`` of a frame with ``nz_glob`` planes."""
 

@@ -90,6 +90,24 @@ def _worker(rank, world, port, out_dir):
                 ranked = torch.where(canon > 0, torch.searchsorted(all_ids, canon.reshape(-1)).reshape(canon.shape) + 1,
                                      torch.zeros_like(canon)).numpy()
                 assert np.array_equal(ranked, ref[z0:z1]), (kind, full, rank)
+        # threshold sampling of the global flattened frame (labelling.py:385-438) from slabs
+        from nellie_b200.sharded_label import sharded_sample_nonzero
+        from oracle import pipeline as P
+        rng = np.random.default_rng(5)
+        for shape, n_samp, sparse in [((23, 20, 24), 500, False), ((17, 9, 11), 100, True), ((12, 8, 9), 10 ** 6, False),
+                                      ((31, 16, 18), 50, True)]:
+            fr = rng.random(shape).astype(np.float32)
+            if sparse:                                  # positives so rare that the strided offsets miss them
+                fr[rng.random(shape) < 0.995] = 0.0
+            fr[rng.random(shape) < 0.3] = 0.0
+            raw = rng.random(shape).astype(np.float32)
+            z0, z1 = z_partition(shape[0], world)[rank]
+            spec = P.FrameSpec(dim_res={"X": 1.0, "Y": 1.0, "Z": 1.0, "T": 1.0}, no_z=False, threshold_sampling_pixels=n_samp)
+            for gate in (None, 0.4):
+                want = P.label_sample(fr, spec, raw if gate is not None else None, gate)
+                got = sharded_sample_nonzero(torch.from_numpy(fr[z0:z1]), z0, shape[0], n_samp,
+                                             torch.from_numpy(raw[z0:z1]) if gate is not None else None, gate).numpy()
+                assert np.array_equal(got, want), (shape, n_samp, gate, rank, got.size, want.size)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
