@@ -48,6 +48,39 @@ def cuda_local_label(mask: torch.Tensor, full_conn: bool) -> Tuple[torch.Tensor,
     return out, int(n.item())
 
 
+def cuda_threshold_from_samples(samples: torch.Tensor, log_domain: bool) -> Optional[float]:
+    """min(triangle, Otsu) of the gathered sample through the same device kernels as the single-GPU path
+    (``LabelEngine.frangi_threshold`` / ``intensity_otsu``: labelling.py:440-465): ``log_domain`` = thresholds of
+    log10(sample), returned as 10**t (Frangi); else plain Otsu (intensity).  None for an empty sample.
+    Every rank calls it on the same gathered sample and gets the same scalar.  (Composition of verified C-ABI calls;
+    not yet run in a multi-GPU job.)"""
+    import ctypes as C
+
+    from . import _cabi
+    lib = _cabi.load()
+    n = int(samples.numel())
+    if n == 0:
+        return None
+    dev = samples.device
+    vals = samples.to(torch.float32).contiguous()
+    hist = torch.zeros(_cabi.HIST_WORDS, dtype=torch.int64, device=dev)
+    thr = torch.zeros(5, dtype=torch.float64, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())                                     # noqa: E731
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        tf = _cabi.TF_LOG10 if log_domain else _cabi.TF_NONE
+        _cabi.call("nb200_hist_reset", vp(hist), st)
+        _cabi.call("nb200_hist_minmax", vp(vals), n, tf, None, vp(hist), st)
+        _cabi.call("nb200_hist_bins", vp(vals), n, tf, None, vp(hist), st)
+        _cabi.call("nb200_finalize_label_threshold", vp(hist), int(bool(log_domain)), vp(thr), st)
+    out = thr.cpu().numpy()
+    if out[3] != 0.0:
+        return None
+    if out[4] != 0.0:
+        raise ValueError("attempt to get argmax of an empty sequence")           # what the reference raises
+    return float(np.float32(out[0]))
+
+
 def _all_gather_ragged(t: torch.Tensor, group=None) -> torch.Tensor:
     """Concatenation over ranks of 1-D / 2-D int64 tensors of different lengths (dim 0)."""
     world = dist.get_world_size(group)
@@ -241,3 +274,24 @@ class ZShardedLabeller:
             pos = torch.searchsorted(all_ids, comp2.reshape(-1)).clamp_(max=all_ids.numel() - 1).reshape(comp2.shape)
             labels = torch.where(comp2 > 0, (pos + 1).to(torch.int32), labels)
         return labels
+
+
+def label_frame_z_sharded(frangi_slab: torch.Tensor, z0: int, nz_glob: int, min_area: int, sampling_pixels: int = 1_000_000,
+                          raw_slab: Optional[torch.Tensor] = None, otsu_thresh_intensity: bool = False,
+                          threshold: Optional[float] = None, group=None) -> torch.Tensor:
+    """``_compute_frame_thresholds`` + ``_run_frame_full_volume`` (labelling.py:511-556) for one Z slab on CUDA: the
+    thresholds come from the all-gathered strided sample, the labels from :class:`ZShardedLabeller`.  Returns the int32
+    labels of the slab, numbered as the single-GPU path numbers the whole frame."""
+    nz, ny, nx = (int(v) for v in frangi_slab.shape)
+    it = None
+    if otsu_thresh_intensity:
+        it = cuda_threshold_from_samples(sharded_sample_nonzero(raw_slab.to(torch.float32), z0, nz_glob, sampling_pixels,
+                                                                 group=group), log_domain=False) or 0
+    elif threshold is not None:
+        it = threshold
+    gate = raw_slab.to(torch.float32) if it is not None else None
+    ft = cuda_threshold_from_samples(sharded_sample_nonzero(frangi_slab, z0, nz_glob, sampling_pixels, gate, it, group=group),
+                                     log_domain=True)
+    frangi = frangi_slab if it is None else frangi_slab * (gate > np.float32(it))           # labelling.py:550-552
+    mask = torch.zeros_like(frangi, dtype=torch.bool) if ft is None else frangi > np.float32(ft)
+    return ZShardedLabeller(z0, nz, nz_glob, ny, nx, cuda_local_label, group).label(mask, min_area)
