@@ -369,6 +369,7 @@ class FrangiEngine3D:
                 src = self._blur_sigma(i, src, {})
                 self._analyse_sigma(i, self.gauss[src])
             self.cur = src
+            self._remove_edges()
             return
         side = self.side_stream
         side.wait_stream(main)                       # the frame has been loaded on the caller's stream
@@ -386,6 +387,14 @@ class FrangiEngine3D:
             last_reader[src] = ev_read
         main.wait_stream(side)
         self.cur = src
+        self._remove_edges()
+
+    def _remove_edges(self):
+        """filtering.py:931-932: optional (off by default) zeroing of the top / bottom rows of every slice's bounding box,
+        applied to the owned planes of the accumulator before _mask_volume (per-slice: no exchange between slabs)."""
+        if self.p.remove_edges:
+            from .edges import remove_edge_bands_
+            remove_edge_bands_(self.acc[self.pad_lo:self.pad_lo + self.nz_own])
 
     def finalize(self, apply_mask_volume=True, out=None):
         """filtering.py:926 (V*masks) + :1014-1018 / :952-967 (_mask_volume).  ``out``: optional device buffer of
@@ -415,8 +424,6 @@ class FrangiEngine3D:
 
     def filter_frame(self, frame: torch.Tensor, apply_mask_volume=True, out=None) -> torch.Tensor:
         """Device tensor in, device tensor out (the engine's own output buffer unless ``out`` is given)."""
-        if self.p.remove_edges:
-            raise NotImplementedError("remove_edges (filtering.py:969-1000) is not implemented on the B200 path yet")
         self.load_frame(frame)
         self.run_sigmas()
         return self.finalize(apply_mask_volume, out=out)

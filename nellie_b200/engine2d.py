@@ -104,8 +104,6 @@ class FrangiEngine2D:
         """One 2-D frame.  A 2048^2 frame is ~180 small kernels (3 ms of GPU time, launch-bound), so from the third
         call on the whole per-frame sequence is replayed as ONE CUDA graph (captured on the second call, after an
         eager warm-up; all buffers are engine-owned and static, only the upload of the frame stays outside)."""
-        if self.p.remove_edges:
-            raise NotImplementedError("remove_edges (filtering.py:969-1000) is not implemented on the B200 path yet")
         key = bool(apply_mask_volume)
         self.gauss[0].copy_(frame)
         if not self.use_graph:
@@ -182,6 +180,9 @@ class FrangiEngine2D:
             self._call("nb200_log2d_accumulate", _ptr(a), _ptr(b), _ptr(self.acc), float(np.float32(float(s) ** 2)),
                        int(i == 0), self.n, _ptr(self.L), st)
         self._call("nb200_log2d_combine", _ptr(self.acc), _ptr(self.L), self.n, _ptr(self.word), _ptr(self.v), st)
+        if self.p.remove_edges:                 # filtering.py:931-932 (off by default)
+            from .edges import remove_edge_bands_
+            remove_edge_bands_(self.v)
         if not apply_mask_volume:
             return self.v
         return self.mask_volume(self.v)

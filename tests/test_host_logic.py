@@ -222,3 +222,33 @@ def test_library_sass_uses_tma_and_packed_f32():
     assert gauss, "blur kernels not found in the library"
     for b in gauss:
         assert "DADD" in b and "DMUL" in b and "DFMA" not in b, b.split("\n")[0]
+
+
+def test_remove_edge_bands_matches_the_reference_loop():
+    """nellie_b200/edges.py against the oracle's restatement of filtering.py:969-1000, 3-D (per slice) and 2-D,
+    with empty slices, boxes lower than the margin, dead (-1) voxels and responses touching the frame border."""
+    import torch
+    from nellie_b200.edges import remove_edge_bands_
+    from oracle import pipeline as P
+    rng = np.random.default_rng(3)
+    for shape in [(6, 50, 20), (4, 17, 9), (1, 40, 8), (3, 12, 5)]:
+        v = np.zeros(shape, np.float32)
+        for z in range(shape[0]):
+            if z == 1:
+                continue                                         # an empty slice
+            r0 = int(rng.integers(0, shape[1] - 2))
+            r1 = int(rng.integers(r0, shape[1]))
+            v[z, r0:r1 + 1] = rng.random((r1 + 1 - r0, shape[2])) * (rng.random((r1 + 1 - r0, shape[2])) < 0.4)
+            v[z, r0, 0] = 1.0
+            v[z, r1, -1] = 1.0
+        spec3 = P.FrameSpec(dim_res={"X": 1.0, "Y": 1.0, "Z": 1.0, "T": 1.0}, no_z=False)
+        want = P.remove_edges(v.copy(), spec3)
+        acc = v.copy()
+        acc[(v == 0) & (rng.random(shape) < 0.5)] = -1.0        # the engines' "dead voxel" marker
+        got = remove_edge_bands_(torch.from_numpy(acc)).numpy()
+        assert np.array_equal(np.maximum(got, 0.0), want), shape
+        spec2 = P.FrameSpec(dim_res={"X": 1.0, "Y": 1.0, "T": 1.0}, no_z=True)
+        want2 = P.remove_edges(v[0].copy(), spec2)
+        got2 = remove_edge_bands_(torch.from_numpy(v[0].copy())).numpy()
+        assert np.array_equal(got2, want2), shape
+    assert not remove_edge_bands_(torch.zeros((3, 8, 8))).any()
