@@ -355,11 +355,11 @@ class FrangiEngine3D:
     def run_sigmas(self):
         """filtering.py:814-851 for every sigma; leaves max-over-sigma / dead flags in ``acc``.
 
-        The blur of sigma i+1 only needs the blurred volume of sigma i, so it runs on a side stream while the
-        caller's stream does K2 / thresholds / K3 of sigma i: the bandwidth-bound Z pass and the FP64-bound Y+X
-        pass fill the issue slots and the HBM bandwidth that the issue-bound Hessian march leaves idle.  Three
-        blur volumes rotate (source of truth of sigma i, scratch, result of sigma i+1); CUDA events order the
-        reuse.  Per-sigma results do not depend on the overlap (same kernels, same inputs)."""
+        Default: blur, then K2 / thresholds / K3, sigma after sigma on the caller's stream.  With ``overlap_blur``
+        the blur of sigma i+1 (which only needs the blurred volume of sigma i) is issued on a side stream under
+        K2 / K3 of sigma i; three blur volumes rotate (source of truth of sigma i, scratch, result of sigma i+1) and
+        CUDA events order their reuse.  Results are identical either way; on B200 the overlap buys nothing because
+        K2 leaves no registers for a second kernel on the SM (see ``__init__``)."""
         main = torch.cuda.current_stream(self.device)
         self.acc.zero_()
         nsig = len(self.steps)
