@@ -73,7 +73,14 @@ typedef struct nb200_vol {
 #define NB200_SP_UNSAFE 9     /* 1.0 when the blurred volume holds values outside the exponent range the fast
                                  constant-divisor division was verified on: kernels fall back to IEEE division */
 #define NB200_SP_FROBSQ_MIN 10 /* smallest frob_sq whose sqrt(.)/max_abs exceeds fl32(cut): mask = frob_sq >= this */
-#define NB200_SP_WORDS 12
+/* words written by nb200_finalize_frob_fast for nb200_frangi_fast (approximate classification with proven margins) */
+#define NB200_SP_AMBIG 11     /* 1.0 when the bounds frob_max in [1, 3] cannot decide whether the mask is empty:
+                                 nb200_hessian_stats_ambig + nb200_finalize_frob_resolve settle it exactly */
+#define NB200_SP_FS_LO 12     /* approximate frob_sq below this: the voxel surely fails the mask */
+#define NB200_SP_FS_HI 13     /* approximate frob_sq at or above this: the voxel surely passes the mask */
+#define NB200_SP_ZT_C 14      /* margin subtracted from the approximate diagonal pair sums (provably-zero test) */
+#define NB200_SP_DELTA 15     /* proven bound of |approximate - reference| for every Hessian entry of this sigma */
+#define NB200_SP_WORDS 20
 
 /* int64[NB200_HS_WORDS] device record reduced by nb200_hessian_stats */
 #define NB200_HS_MAX_ABS_BITS 0   /* float bits of max|H| */
@@ -81,7 +88,10 @@ typedef struct nb200_vol {
 #define NB200_HS_MIN_NZ_COMPL 2   /* 0x7f800000 - float bits of the smallest non-zero |blurred value| (0 = none seen);
                                      complemented so that every word of the record reduces with MAX */
 #define NB200_HS_MAX_G_BITS 3     /* float bits of the largest |blurred value| */
-#define NB200_HS_WORDS 4
+#define NB200_HS_APPROX_MAX_BITS 4 /* nb200_hessian_stats_fast: float bits of the approximate max|H| of the interior */
+#define NB200_HS_FALLBACK 5       /* nb200_hessian_stats_fast: 1 when its exactness argument does not apply to this
+                                     volume (nb200_finalize_max_abs then sets sp[UNSAFE]: the exact passes take over) */
+#define NB200_HS_WORDS 8
 
 int nb200_abi_version(void);
 const char* nb200_last_error(void);
@@ -160,6 +170,39 @@ int nb200_hessian_stats_code(const float* gauss, const nb200_vol* vol, const flo
 int nb200_hessian_stats_redo(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
                              const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
                              float* code, void* stream);
+/* Exact statistics pass that only runs when nb200_finalize_frob_fast left sp[NB200_SP_AMBIG] set (and the redo pass
+ * has not run): provides the exact max frob_sq for nb200_finalize_frob_resolve. */
+int nb200_hessian_stats_ambig(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
+                              const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
+                              void* stream);
+
+/* ---- F4, fast form: the same statistics from an APPROXIMATE Hessian with proven error bounds ---------------
+ * (filtering.py:446-562).  The interior march evaluates the six second differences with plain float32
+ * subtractions (no divisions), keeps per-warp maxima, and appends every sub-chunk whose maximum is within 2^-10 of
+ * the running maximum to a work list; a second kernel re-evaluates the listed sub-chunks that can hold the true
+ * maximum (approximate maximum minus twice the proven error bound) with the reference's exact arithmetic, so
+ * hstats[MAX_ABS_BITS] ends up bit-identical to nb200_hessian_stats.  sqrt(frob_sq) at the lattice points is
+ * evaluated exactly inside the march; the border shell runs through the exact per-voxel kernel.  max frob_sq is NOT
+ * produced (see nb200_finalize_frob_fast).  When the argument does not apply (value range outside the verified
+ * exponents, error bound not small against the maximum, work list overflow) hstats[FALLBACK] is set and
+ * nb200_finalize_max_abs raises sp[UNSAFE], which makes nb200_hessian_stats_redo recompute everything exactly.
+ * Requires nx % 4 == 0, 16-byte aligned gauss, div_mode FAST or POW2 (NB200_ERR_UNSUPPORTED otherwise: use
+ * nb200_hessian_stats_code).  workspace: nb200_hessian_fast_workspace_bytes() bytes of device memory. */
+size_t nb200_hessian_fast_workspace_bytes(void);
+int nb200_hessian_stats_fast(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
+                             int sz, int sy, int sx, float* frob_samples, long long* hstats, void* workspace,
+                             void* stream);
+/* Frobenius threshold for the fast path: as nb200_finalize_frob, but without max frob_sq.  Emptiness of the mask
+ * follows from the bounds 1 <= max frob <= 3 (the voxel attaining max|H| has frob >= 1; frob_sq <= 9 max|H|^2);
+ * when the cut falls between them sp[AMBIG] is set.  Also writes the classification thresholds
+ * sp[FS_LO], sp[FS_HI], sp[ZT_C], sp[DELTA] from the proven error bound delta = 40 * 2^-24 * max|g| * max_scale
+ * (max_scale = largest 1/(fl32(2h_a) * fl32(2h_b))).  mask_enabled = 0: every voxel passes (Filter mask=False).
+ * max_scale = 0 selects the plain nb200_finalize_frob behaviour (exact max frob_sq in hstats) with the mask switch. */
+int nb200_finalize_frob_fast(const long long* state, const long long* hstats, double fixed_thresh, double division,
+                             double max_scale, int mask_enabled, double* sp, void* stream);
+/* After nb200_hessian_stats_ambig: sp[SKIP] from the exact max frob_sq when sp[AMBIG] was set. */
+int nb200_finalize_frob_resolve(const long long* hstats, double* sp, void* stream);
+
 /* Division mode for one grid-spacing divisor d = fl32(h) or fl32(2h) (synchronous, init time only):
  *   2 (NB200_DIV_POW2)  d is a power of two: multiply by the exact reciprocal;
  *   1 (NB200_DIV_FAST)  q = fma(fma(-n*r, d, n), r, n*r), r = RN(1/d), verified HERE bit-for-bit against IEEE
@@ -189,6 +232,20 @@ int nb200_frangi_accumulate(const float* gauss, float* acc, const nb200_vol* vol
 int nb200_frangi_sparse(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
                         const float* spacing, int div_mode, float alpha_sq, float beta_sq, const double* sp,
                         unsigned* list, long long list_capacity, unsigned long long* counter, void* stream);
+/* ---- F4-F9 fused, fast form ---------------------------------------------------------------------------------
+ * One Z-march over the blurred volume (TMA ring, no CTA barrier): the approximate Hessian classifies every live
+ * voxel as surely failing the mask (acc = -1), surely passing with a provably zero response (nothing to do), or
+ * candidate; candidates get the reference's exact Hessian from the staged planes, the exact mask test, the exact
+ * provably-zero tests, and the survivors the float64 eigenvalues + vesselness, all inside the same kernel
+ * (per-warp queues, full warps).  Results are bit-identical to nb200_frangi_accumulate.  Returns at once when
+ * sp[SKIP] or sp[UNSAFE] is set (the caller then runs nb200_frangi_sparse_gated).  Same requirements as
+ * nb200_hessian_stats_fast.  diag: optional device uint64[8] counters (tests / profiling). */
+int nb200_frangi_fast(const float* gauss, float* acc, const nb200_vol* vol, const float* spacing, int div_mode,
+                      float alpha_sq, float beta_sq, const double* sp, unsigned long long* diag, void* stream);
+/* nb200_frangi_sparse that only runs when sp[UNSAFE] is set (fallback of nb200_frangi_fast). */
+int nb200_frangi_sparse_gated(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
+                              const float* spacing, int div_mode, float alpha_sq, float beta_sq, const double* sp,
+                              unsigned* list, long long list_capacity, unsigned long long* counter, void* stream);
 /*   list / counter (optional scratch): device buffer of `list_capacity` uint32 (>= voxels of [zc0,zc1)) and one
  *   device uint64.  With them (and a buffer below 2^32 voxels) the step runs as a barrier-free stream kernel that
  *   appends the candidates to the list plus a solve kernel that walks it; without, as one kernel with

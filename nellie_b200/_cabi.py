@@ -11,9 +11,11 @@ import os
 from . import build as _build
 
 HIST_WORDS = 3 + 256
-SP_WORDS = 12
-HS_WORDS = 4
+SP_WORDS = 20
+HS_WORDS = 8
 SP_GAMMA, SP_GAMMA_SQ, SP_FROB_THR, SP_FROB_CUT, SP_MAX_ABS, SP_SKIP, SP_STATUS, SP_TRI, SP_OTSU, SP_UNSAFE = range(10)
+SP_FROBSQ_MIN, SP_AMBIG, SP_FS_LO, SP_FS_HI, SP_ZT_C, SP_DELTA = range(10, 16)
+HS_MAX_ABS_BITS, HS_MAX_FROBSQ_BITS, HS_MIN_NZ_COMPL, HS_MAX_G_BITS, HS_APPROX_MAX_BITS, HS_FALLBACK = range(6)
 DIV_IEEE, DIV_FAST, DIV_POW2 = 0, 1, 2
 TF_NONE, TF_DIV, TF_LOG10 = 0, 1, 2
 SELECT_WORDS = 2048 + 8
@@ -64,6 +66,16 @@ _SIGS = {
                                   _p, _p], C.c_int),
     "nb200_frangi_sparse": ([_p, _p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, _p, _p, _ll, _p, _p],
                             C.c_int),
+    "nb200_frangi_sparse_gated": ([_p, _p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, _p, _p, _ll, _p,
+                                   _p], C.c_int),
+    "nb200_hessian_stats_ambig": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p],
+                                  C.c_int),
+    "nb200_hessian_fast_workspace_bytes": ([], C.c_size_t),
+    "nb200_hessian_stats_fast": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p],
+                                 C.c_int),
+    "nb200_finalize_frob_fast": ([_p, _p, C.c_double, C.c_double, C.c_double, C.c_int, _p, _p], C.c_int),
+    "nb200_finalize_frob_resolve": ([_p, _p, _p], C.c_int),
+    "nb200_frangi_fast": ([_p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, _p, _p, _p], C.c_int),
     "nb200_hessian_components": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, _p], C.c_int),
     "nb200_divisor_mode": ([C.c_float, C.POINTER(C.c_int), _p], C.c_int),
     "nb200_hstats_reset": ([_p, _p], C.c_int),

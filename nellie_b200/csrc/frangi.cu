@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "hessian.cuh"
 #include "hessian_march.cuh"
+#include "march_host.cuh"
 
 namespace {
 
@@ -432,9 +433,13 @@ march_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     if (flags != nullptr) {
         if (check_skip && flags[NB200_SP_SKIP] != 0.0) return;   // empty mask: the sigma contributes nothing (:843-844)
-        // the fast-division launch and its IEEE twin are both enqueued; exactly one of them does the work
+        // the fast-division launch and its IEEE twin are both enqueued; exactly one of them does the work.
+        // run_if_unsafe: -1 always, 0 / 1 = only when sp[UNSAFE] is clear / set, 2 = only when the emptiness of the
+        // Frobenius mask is still undecided (sp[AMBIG] set and no exact pass has run: UNSAFE clear)
         const bool unsafe = flags[NB200_SP_UNSAFE] != 0.0;
-        if (run_if_unsafe >= 0 && unsafe != (run_if_unsafe != 0)) return;
+        if (run_if_unsafe == 2) {
+            if (unsafe || flags[NB200_SP_AMBIG] == 0.0) return;
+        } else if (run_if_unsafe >= 0 && unsafe != (run_if_unsafe != 0)) return;
     }
     hm::Smem& s = *reinterpret_cast<hm::Smem*>(smem_raw);
     const int ntx = (v.nx + hm::TX - 1) / hm::TX, nty = (v.ny - 4 + hm::TYO - 1) / hm::TYO;
@@ -551,8 +556,10 @@ __device__ __forceinline__ ShellHessian shell_hessian(const float* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256)
-shell_stats_kernel(const float* __restrict__ g, Shell sh, nb::Spacing3 sp, StatsParams p, const double* run_flag) {
-    if (run_flag != nullptr && *run_flag == 0.0) return;     // redo pass: only when the fast division was unsafe
+shell_stats_kernel(const float* __restrict__ g, Shell sh, nb::Spacing3 sp, StatsParams p, const double* spd, int gate) {
+    // gate: -1 always; 1 = redo pass (only when sp[UNSAFE]); 2 = only when sp[AMBIG] and not sp[UNSAFE]
+    if (gate == 1 && spd[NB200_SP_UNSAFE] == 0.0) return;
+    if (gate == 2 && (spd[NB200_SP_UNSAFE] != 0.0 || spd[NB200_SP_AMBIG] == 0.0)) return;
     float m_abs = 0.0f, m_frob = 0.0f, g_min = INFINITY, g_max = 0.0f;
     const long long total = sh.n1 + sh.n2 + sh.n3;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -731,6 +738,8 @@ __global__ void hstats_reset_kernel(long long* hstats) {
     if (threadIdx.x < NB200_HS_WORDS) hstats[threadIdx.x] = 0;
 }
 
+}  // namespace
+namespace nb {
 int check_vol(const nb200_vol& v, const char* who) {
     NB_REQUIRE(v.ny >= 2 && v.nx >= 2 && v.nz_glob >= 2, NB200_ERR_ARG,
                "%s: every axis needs >= 2 samples (numpy.gradient)", who);
@@ -742,6 +751,9 @@ int check_vol(const nb200_vol& v, const char* who) {
                NB200_ERR_ARG, "%s: Z halo of 2 planes missing", who);
     return NB200_OK;
 }
+}  // namespace nb
+namespace {
+using nb::check_vol;
 
 hm::Divs divs_from(const float* s) {
     hm::Divs dv;
@@ -780,6 +792,8 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
+}  // namespace
+namespace nb {
 // returns true when `map` describes g for TMA; false -> the kernel uses plain loads
 bool make_plane_map(const float* g, const nb200_vol& v, CUtensorMap* map) {
     memset(map, 0, sizeof(*map));
@@ -796,16 +810,19 @@ bool make_plane_map(const float* g, const nb200_vol& v, CUtensorMap* map) {
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
+}  // namespace nb
+namespace {
+using nb::make_plane_map;
+using nb::MarchPlan;
+using nb::plan_march;
 
 template <class Epi>
 constexpr size_t smem_bytes_for() { return sizeof(hm::Smem); }
 template <>
 constexpr size_t smem_bytes_for<FrangiEpi>() { return sizeof(hm::Smem) + sizeof(FrangiQueue); }
 
-struct MarchPlan {
-    int zi0, zi1, zchunk;     // interior planes (GLOBAL coordinates) and chunk length
-    long long n_ctas;
-};
+}  // namespace
+namespace nb {
 // Interior of the compute window; Z chunks sized for several waves of 2 CTAs/SM, no shorter than 32 planes
 MarchPlan plan_march(const nb200_vol& v) {
     MarchPlan m;
@@ -827,6 +844,8 @@ MarchPlan plan_march(const nb200_vol& v) {
     m.n_ctas = tiles * chunks;
     return m;
 }
+}  // namespace nb
+namespace {
 
 template <int MODE, class Epi, class Params>
 int launch_one(const float* g, const nb200_vol& v, const CUtensorMap& map, bool use_tma, const MarchPlan& m,
@@ -852,7 +871,7 @@ int launch_one(const float* g, const nb200_vol& v, const CUtensorMap& map, bool 
 // one that runs
 // twin: 0 = fast launch (runs unless sp[UNSAFE]) + IEEE twin (runs if sp[UNSAFE]);  1 = fast launch only,
 // unconditional (K2's first pass, which also measures the value range the flag is derived from);
-// 2 = IEEE twin only (K2's redo pass)
+// 2 = exact redo pass, runs if sp[UNSAFE];  3 = exact pass that runs if sp[AMBIG] (and not UNSAFE)
 template <class Epi, class Params>
 int launch_march(const float* g, const nb200_vol& v, const float* spacing, int div_mode, const double* sp,
                  int check_skip, const Params& p, cudaStream_t st, const char* what, int twin = 0) {
@@ -861,10 +880,18 @@ int launch_march(const float* g, const nb200_vol& v, const float* spacing, int d
     CUtensorMap map;
     const bool use_tma = make_plane_map(g, v, &map);
     int rc;
-    if (div_mode == hm::DIV_POW2) rc = launch_one<hm::DIV_POW2, Epi>(g, v, map, use_tma, m, spacing, sp, -1, check_skip, p, st);
+    if (twin == 2 || twin == 3) {
+        // gated passes: 2 = exact redo when sp[UNSAFE] (IEEE division replaces the fast sequence), 3 = exact pass when
+        // the emptiness of the mask is undecided (sp[AMBIG], UNSAFE clear: the native mode is valid)
+        const int gate = twin == 2 ? 1 : 2;
+        if (sp == nullptr) return NB200_OK;
+        if (div_mode == hm::DIV_POW2) rc = launch_one<hm::DIV_POW2, Epi>(g, v, map, use_tma, m, spacing, sp, gate, check_skip, p, st);
+        else if (div_mode == hm::DIV_FAST && twin == 3) rc = launch_one<hm::DIV_FAST, Epi>(g, v, map, use_tma, m, spacing, sp, gate, check_skip, p, st);
+        else rc = launch_one<hm::DIV_IEEE, Epi>(g, v, map, use_tma, m, spacing, sp, gate, check_skip, p, st);
+    }
+    else if (div_mode == hm::DIV_POW2) rc = launch_one<hm::DIV_POW2, Epi>(g, v, map, use_tma, m, spacing, sp, -1, check_skip, p, st);
     else if (div_mode == hm::DIV_IEEE || sp == nullptr) rc = launch_one<hm::DIV_IEEE, Epi>(g, v, map, use_tma, m, spacing, sp, -1, check_skip, p, st);
     else if (twin == 1) rc = launch_one<hm::DIV_FAST, Epi>(g, v, map, use_tma, m, spacing, sp, -1, check_skip, p, st);
-    else if (twin == 2) rc = launch_one<hm::DIV_IEEE, Epi>(g, v, map, use_tma, m, spacing, sp, 1, check_skip, p, st);
     else {
         rc = launch_one<hm::DIV_FAST, Epi>(g, v, map, use_tma, m, spacing, sp, 0, check_skip, p, st);
         if (rc == NB200_OK) rc = launch_one<hm::DIV_IEEE, Epi>(g, v, map, use_tma, m, spacing, sp, 1, check_skip, p, st);
@@ -878,6 +905,42 @@ unsigned shell_grid(const Shell& sh) {
 }
 
 }  // namespace
+
+namespace nb {
+int launch_shell_stats(const float* g, const nb200_vol& v, const float* spacing, int sz, int sy, int sx,
+                       float* frob_samples, long long* hstats, float* code, const double* sp, int gate,
+                       cudaStream_t st) {
+    StatsParams p;
+    p.sz = sz; p.sy = sy; p.sx = sx;
+    const int g0 = v.zc0 + v.zg_off;
+    p.g_first = ((g0 + sz - 1) / sz) * sz;
+    p.ly_n = (v.ny + sy - 1) / sy;
+    p.lx_n = (v.nx + sx - 1) / sx;
+    p.frob_samples = frob_samples;
+    p.hstats = hstats;
+    p.code = code;
+    p.code_vec_ok = 0;
+    const Shell sh = make_shell(v);
+    if (sh.n1 + sh.n2 + sh.n3 <= 0) return NB200_OK;
+    shell_stats_kernel<<<shell_grid(sh), 256, 0, st>>>(g, sh, spacing3_from(spacing), p, sp, sp ? gate : -1);
+    return nb::check_launch("hessian_stats(shell)");
+}
+
+int launch_shell_frangi(const float* g, float* acc, const nb200_vol& v, const float* spacing, float alpha_sq,
+                        float beta_sq, const double* sp, cudaStream_t st) {
+    FrangiParams p;
+    p.acc = acc;
+    p.alpha_sq = alpha_sq;
+    p.beta_sq = beta_sq;
+    p.spd = sp;
+    p.acc_vec_ok = 0;
+    p.debug = 0;
+    const Shell sh = make_shell(v);
+    if (sh.n1 + sh.n2 + sh.n3 <= 0) return NB200_OK;
+    shell_frangi_kernel<<<shell_grid(sh), 256, 0, st>>>(g, sh, spacing3_from(spacing), p);
+    return nb::check_launch("frangi_accumulate(shell)");
+}
+}  // namespace nb
 
 extern "C" {
 
@@ -915,7 +978,8 @@ int nb200_hessian_stats(const float* gauss, const nb200_vol* vol, const float* s
 }
 
 namespace {
-// pass 0 = first (fast division unconditional when div_mode is FAST), pass 1 = redo with IEEE if sp[UNSAFE]
+// pass 0 = first (fast division unconditional when div_mode is FAST), pass 1 = exact redo if sp[UNSAFE] (IEEE division
+// when the mode was FAST), pass 2 = exact statistics if sp[AMBIG] (max frob_sq decides whether the mask is empty)
 int hessian_stats_impl(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode, const double* sp,
                        int sz, int sy, int sx, float* frob_samples, long long* hstats, float* code, void* stream,
                        int pass) {
@@ -927,7 +991,7 @@ int hessian_stats_impl(const float* gauss, const nb200_vol* vol, const float* sp
     int rc = check_vol(v, "nb200_hessian_stats");
     if (rc) return rc;
     if (v.zc0 == v.zc1) return NB200_OK;
-    if (pass == 1 && (div_mode != hm::DIV_FAST || sp == nullptr)) return NB200_OK;   // nothing to redo
+    if (pass != 0 && sp == nullptr) return NB200_OK;   // nothing to gate on
     StatsParams p;
     p.sz = sz; p.sy = sy; p.sx = sx;
     const int g0 = v.zc0 + v.zg_off;
@@ -944,17 +1008,13 @@ int hessian_stats_impl(const float* gauss, const nb200_vol* vol, const float* sp
         rc = nb::check_launch("hessian_stats(redo reset)");
         if (rc) return rc;
     }
-    rc = launch_march<StatsEpi>(gauss, v, spacing, div_mode, sp, 0, p, st, "hessian_stats", pass == 0 ? 1 : 2);
+    rc = launch_march<StatsEpi>(gauss, v, spacing, div_mode, sp, 0, p, st, "hessian_stats", pass + 1);
     if (rc) return rc;
-    const Shell sh = make_shell(v);
-    if (sh.n1 + sh.n2 + sh.n3 > 0) {
-        shell_stats_kernel<<<shell_grid(sh), 256, 0, st>>>(gauss, sh, spacing3_from(spacing), p,
-                                                          pass == 1 ? sp + NB200_SP_UNSAFE : nullptr);
-        rc = nb::check_launch("hessian_stats(shell)");
-    }
-    return rc;
+    return nb::launch_shell_stats(gauss, v, spacing, sz, sy, sx, frob_samples, hstats, code, sp,
+                                  pass == 0 ? -1 : pass, st);
 }
 }  // namespace
+
 
 int nb200_hessian_stats_code(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
                              const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
@@ -966,6 +1026,12 @@ int nb200_hessian_stats_redo(const float* gauss, const nb200_vol* vol, const flo
                              const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
                              float* code, void* stream) {
     return hessian_stats_impl(gauss, vol, spacing, div_mode, sp, sz, sy, sx, frob_samples, hstats, code, stream, 1);
+}
+
+int nb200_hessian_stats_ambig(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode,
+                              const double* sp, int sz, int sy, int sx, float* frob_samples, long long* hstats,
+                              void* stream) {
+    return hessian_stats_impl(gauss, vol, spacing, div_mode, sp, sz, sy, sx, frob_samples, hstats, nullptr, stream, 2);
 }
 
 int nb200_hessian_components(const float* gauss, const nb200_vol* vol, const float* spacing, int div_mode, float* out6,

@@ -46,6 +46,7 @@ struct SparseParams {
     int div_mode;
     int nbx, nby, nbz;
     int bz;                 // brick depth in planes
+    int only_if_unsafe;     // fallback of nb200_frangi_fast: run only when sp[UNSAFE] is set
 };
 
 struct GlobalLoad3 {
@@ -117,6 +118,7 @@ __device__ __forceinline__ void candidate_hessian(const SparseParams& p, long lo
 __global__ void __launch_bounds__(NT, 3)
 frangi_sparse_kernel(const SparseParams p) {
     if (p.spd[NB200_SP_SKIP] != 0.0) return;            // empty mask: the sigma contributes nothing (:843-844)
+    if (p.only_if_unsafe && p.spd[NB200_SP_UNSAFE] == 0.0) return;
     __shared__ Queues q;
     const float gamma_sq = (float)p.spd[NB200_SP_GAMMA_SQ];
     const float fs_min = (float)p.spd[NB200_SP_FROBSQ_MIN];   // mask <=> frob_sq >= fs_min (finalize_frob_kernel)
@@ -294,6 +296,7 @@ constexpr int WSTAGE = 256;                 // per-warp staging slots (flush at 
 __global__ void __launch_bounds__(NT)
 sparse_stream_kernel(const SparseParams p, unsigned* __restrict__ list, unsigned long long* __restrict__ counter) {
     if (p.spd[NB200_SP_SKIP] != 0.0) return;
+    if (p.only_if_unsafe && p.spd[NB200_SP_UNSAFE] == 0.0) return;
     __shared__ unsigned stage[NT / 32][WSTAGE];
     const float fs_min = (float)p.spd[NB200_SP_FROBSQ_MIN];
     const nb200_vol v = p.v;
@@ -380,102 +383,12 @@ sparse_stream_kernel(const SparseParams p, unsigned* __restrict__ list, unsigned
     flush(1);
 }
 
-// Variant with CTA-level staging: the candidates of one group of planes of a brick (8 rows x 128 columns x G planes)
-// are appended to the list as ONE contiguous segment, so the 256 consecutive entries a solve CTA works on come from one
-// compact slab and their stencil reads share L1 lines (per-warp staging scatters a slab's rows over the list).
-// Costs three CTA barriers per group.
-constexpr int SG = 4;                       // planes per group
-__global__ void __launch_bounds__(NT)
-sparse_stream_cta_kernel(const SparseParams p, unsigned* __restrict__ list, unsigned long long* __restrict__ counter) {
-    if (p.spd[NB200_SP_SKIP] != 0.0) return;
-    __shared__ unsigned stage[SG * BX * BY];
-    __shared__ int n_stage;
-    __shared__ unsigned long long g_base;
-    const float fs_min = (float)p.spd[NB200_SP_FROBSQ_MIN];
-    const nb200_vol v = p.v;
-    const long long plane = (long long)v.ny * v.nx;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    if (threadIdx.x == 0) n_stage = 0;
-    __syncthreads();
-    const int tx = 4 * lane;
-    const long long nbricks = (long long)p.nbx * p.nby * p.nbz;
-    for (long long b = blockIdx.x; b < nbricks; b += gridDim.x) {
-        long long r = b;
-        const int bx = (int)(r % p.nbx); r /= p.nbx;
-        const int by = (int)(r % p.nby); r /= p.nby;
-        const int x = bx * BX + tx, y = by * BY + warp;   // one row of the brick per warp
-        const int z0 = v.zc0 + (int)r * p.bz;
-        const int z1 = min(z0 + p.bz, v.zc1);
-        const bool row_in = y < v.ny && x < v.nx;
-        for (int zg0 = z0; zg0 < z1; zg0 += SG) {
-            float4 c[SG], a[SG];
-#pragma unroll
-            for (int i = 0; i < SG; ++i) {
-                const int zb = zg0 + i;
-                c[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                a[i] = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);
-                if (row_in && zb < z1) {
-                    const long long at = (long long)zb * plane + (long long)y * v.nx + x;
-                    if (p.vec_ok) {
-                        c[i] = __ldg(reinterpret_cast<const float4*>(p.code + at));
-                        a[i] = *reinterpret_cast<const float4*>(p.acc + at);
-                    } else {
-                        float* cc = &c[i].x; float* aa = &a[i].x;
-                        for (int k = 0; k < 4; ++k)
-                            if (x + k < v.nx) { cc[k] = __ldg(p.code + at + k); aa[k] = p.acc[at + k]; }
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < SG; ++i) {
-                const int zb = zg0 + i;
-                const float* cc = &c[i].x;
-                float* aa = &a[i].x;
-                unsigned cand = 0, kill = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool alive = aa[k] >= 0.0f;
-                    const bool pass = fabsf(cc[k]) >= fs_min;            // NaN fails, like the reference's comparison
-                    if (alive && !pass) { kill |= 1u << k; aa[k] = -1.0f; }   // dead voxels stay dead (AND of masks)
-                    if (alive && pass && !(__float_as_uint(cc[k]) >> 31)) cand |= 1u << k;
-                }
-                const long long at = (long long)zb * plane + (long long)y * v.nx + x;
-                if (kill) {
-                    if (p.vec_ok) *reinterpret_cast<float4*>(p.acc + at) = a[i];
-                    else for (int k = 0; k < 4; ++k) if ((kill >> k) & 1u) p.acc[at + k] = -1.0f;
-                }
-                if (__any_sync(0xffffffffu, cand != 0u)) {
-                    const unsigned b0 = __ballot_sync(0xffffffffu, cand & 1u), b1 = __ballot_sync(0xffffffffu, cand & 2u);
-                    const unsigned b2 = __ballot_sync(0xffffffffu, cand & 4u), b3 = __ballot_sync(0xffffffffu, cand & 8u);
-                    const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-                    int base = 0;
-                    if (lane == 0) base = atomicAdd(&n_stage, n0 + n1 + n2 + n3);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    const unsigned at32 = (unsigned)at;
-                    if (cand & 1u) stage[base + __popc(b0 & lt)] = at32;
-                    if (cand & 2u) stage[base + n0 + __popc(b1 & lt)] = at32 + 1u;
-                    if (cand & 4u) stage[base + n0 + n1 + __popc(b2 & lt)] = at32 + 2u;
-                    if (cand & 8u) stage[base + n0 + n1 + n2 + __popc(b3 & lt)] = at32 + 3u;
-                }
-            }
-            __syncthreads();                                  // every push of the group is in
-            const int n = n_stage;
-            if (threadIdx.x == 0 && n > 0) g_base = atomicAdd(counter, (unsigned long long)n);
-            __syncthreads();                                  // everyone has read n; g_base is visible
-            if (threadIdx.x == 0) n_stage = 0;
-            const unsigned long long gb = g_base;
-            for (int i = threadIdx.x; i < n; i += NT) list[gb + i] = stage[i];
-            __syncthreads();                                  // stage and counter are free for the next group
-        }
-    }
-}
-
 constexpr int WQ = 64;                      // per-warp survivor queue (< 32 left over + <= 32 pushed)
 
 __global__ void __launch_bounds__(NT, 4)
 sparse_solve_kernel(const SparseParams p, const unsigned* __restrict__ list, const unsigned long long* __restrict__ counter) {
     if (p.spd[NB200_SP_SKIP] != 0.0) return;
+    if (p.only_if_unsafe && p.spd[NB200_SP_UNSAFE] == 0.0) return;
     __shared__ float wq[NT / 32][7][WQ];
     const float gamma_sq = (float)p.spd[NB200_SP_GAMMA_SQ];
     const int div_mode = (p.div_mode == NB200_DIV_FAST && p.spd[NB200_SP_UNSAFE] != 0.0) ? NB200_DIV_IEEE : p.div_mode;
@@ -539,10 +452,11 @@ sparse_solve_kernel(const SparseParams p, const unsigned* __restrict__ list, con
 
 }  // namespace
 
-extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
-                                   const float* spacing, int div_mode, float alpha_sq, float beta_sq, const double* sp,
-                                   unsigned* list, long long list_capacity, unsigned long long* counter,
-                                   void* stream) {
+namespace {
+int frangi_sparse_impl(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
+                       const float* spacing, int div_mode, float alpha_sq, float beta_sq, const double* sp,
+                       unsigned* list, long long list_capacity, unsigned long long* counter,
+                       void* stream, int only_if_unsafe) {
     NB_REQUIRE(gauss && code && acc && vol && spacing && sp, NB200_ERR_ARG, "nb200_frangi_sparse: null argument");
     NB_REQUIRE(div_mode >= 0 && div_mode <= 2, NB200_ERR_ARG, "nb200_frangi_sparse: div_mode %d", div_mode);
     const nb200_vol v = *vol;
@@ -565,6 +479,7 @@ extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float*
         p.sp.r1[a] = 1.0f / spacing[2 * a]; p.sp.r2[a] = 1.0f / spacing[2 * a + 1];
     }
     p.div_mode = div_mode;
+    p.only_if_unsafe = only_if_unsafe;
     p.alpha_sq = alpha_sq; p.beta_sq = beta_sq; p.spd = sp;
     p.vec_ok = (v.nx % 4 == 0) && (((reinterpret_cast<uintptr_t>(acc) | reinterpret_cast<uintptr_t>(code)) & 15) == 0);
     p.nbx = (v.nx + BX - 1) / BX;
@@ -586,9 +501,7 @@ extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float*
         p.nbz = (v.zc1 - v.zc0 + p.bz - 1) / p.bz;
         nbricks = (long long)p.nbx * p.nby * p.nbz;
         const long long cap_s = (long long)(per_sm > 0 ? per_sm : 3) * nb::sm_count();
-        static const int mode = getenv("NB200_STREAM_MODE") ? atoi(getenv("NB200_STREAM_MODE")) : 0;
-        if (mode == 1) sparse_stream_cta_kernel<<<(unsigned)(nbricks < cap_s ? nbricks : cap_s), NT, 0, st>>>(p, list, counter);
-        else sparse_stream_kernel<<<(unsigned)(nbricks < cap_s ? nbricks : cap_s), NT, 0, st>>>(p, list, counter);
+        sparse_stream_kernel<<<(unsigned)(nbricks < cap_s ? nbricks : cap_s), NT, 0, st>>>(p, list, counter);
         int rc = nb::check_launch("frangi_sparse(stream)");
         if (rc) return rc;
         sparse_solve_kernel<<<(unsigned)(4 * nb::sm_count()), NT, 0, st>>>(p, list, counter);
@@ -600,4 +513,21 @@ extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float*
     const long long cap = 3LL * nb::sm_count();
     frangi_sparse_kernel<<<(unsigned)(nbricks < cap ? nbricks : cap), NT, 0, nb::as_stream(stream)>>>(p);
     return nb::check_launch("frangi_sparse");
+}
+}  // namespace
+
+extern "C" int nb200_frangi_sparse(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
+                                   const float* spacing, int div_mode, float alpha_sq, float beta_sq, const double* sp,
+                                   unsigned* list, long long list_capacity, unsigned long long* counter,
+                                   void* stream) {
+    return frangi_sparse_impl(gauss, code, acc, vol, spacing, div_mode, alpha_sq, beta_sq, sp, list, list_capacity, counter,
+                              stream, 0);
+}
+
+extern "C" int nb200_frangi_sparse_gated(const float* gauss, const float* code, float* acc, const nb200_vol* vol,
+                                         const float* spacing, int div_mode, float alpha_sq, float beta_sq,
+                                         const double* sp, unsigned* list, long long list_capacity,
+                                         unsigned long long* counter, void* stream) {
+    return frangi_sparse_impl(gauss, code, acc, vol, spacing, div_mode, alpha_sq, beta_sq, sp, list, list_capacity, counter,
+                              stream, 1);
 }

@@ -271,17 +271,22 @@ __global__ void finalize_max_abs_kernel(const long long* hstats, double* sp) {
     const uint32_t compl_min = (uint32_t)hstats[NB200_HS_MIN_NZ_COMPL];
     const float g_min = compl_min == 0u ? 1.0f : nb::u2f(0x7f800000u - compl_min);
     const float g_max = nb::u2f((uint32_t)hstats[NB200_HS_MAX_G_BITS]);
-    const bool safe = g_min >= 9.313225746154785e-10f && g_max <= 1.152921504606847e18f;
+    // hstats[FALLBACK]: nb200_hessian_stats_fast could not prove its maximum exact for this volume
+    const bool safe = g_min >= 9.313225746154785e-10f && g_max <= 1.152921504606847e18f && hstats[NB200_HS_FALLBACK] == 0;
     sp[NB200_SP_UNSAFE] = safe ? 0.0 : 1.0;
 }
 
+// fast != 0: no exact max frob_sq unless the exact redo pass ran (sp[UNSAFE]); emptiness of the mask from the bounds
+// 1 <= max frob <= 3, classification thresholds of nb200_frangi_fast from the proven error bound (hessian_fast.cu)
 __global__ void finalize_frob_kernel(const long long* state, const long long* hstats, double fixed_thresh,
-                                     double division, double* sp) {
+                                     double division, double* sp, int fast, double max_scale, int mask_enabled) {
     __shared__ double work[4 * NB];
     if (threadIdx.x != 0) return;
     double thr = 0.0;
     double status = sp[NB200_SP_STATUS];
-    if (fixed_thresh == fixed_thresh) {
+    if (!mask_enabled) {
+        thr = 0.0;
+    } else if (fixed_thresh == fixed_thresh) {
         thr = fixed_thresh;
     } else if (state[NB200_HIST_COUNT] > 0) {
         const TwoThresholds t = otsu_triangle(state, work);
@@ -297,7 +302,20 @@ __global__ void finalize_frob_kernel(const long long* state, const long long* hs
     } else {
         cut = thr / division;
     }
+    if (!mask_enabled) cut = -INFINITY;                  // every voxel passes (frob > -inf)
     any = top > (float)cut;     // sqrt and division are monotone: max frob decides emptiness
+    double ambig = 0.0;
+    if (fast && sp[NB200_SP_UNSAFE] == 0.0) {
+        // The voxel attaining max|H| = M has frob_sq >= RN(M*M) (rounding is monotone, all terms are >= 0), hence
+        // frob >= 0.999; every voxel has frob_sq <= 9.0001 M^2, hence frob <= 3.001.
+        const float raw_m = nb::u2f((uint32_t)hstats[NB200_HS_MAX_ABS_BITS]);
+        const float cutf = (float)cut;
+        if (!(raw_m > 0.0f)) any = 0.0f > cutf;          // all-zero Hessian: frob == 0 everywhere
+        else if (cutf < 0.99f) any = true;
+        else if (cutf >= 3.01f) any = false;
+        else { any = true; ambig = 1.0; }                // nb200_finalize_frob_resolve decides with the exact maximum
+    }
+    if (!mask_enabled) { any = true; ambig = 0.0; }
     // K3 tests frob_sq directly: sqrt and the division by max_abs are monotone, so the mask
     // "sqrt(fs)/max_abs > cut" is an up-set {fs >= fs_min}; find its smallest member by bisection over the
     // (ordered) bit patterns of the non-negative floats.  NaN cut -> fs_min = NaN -> nothing passes.
@@ -313,12 +331,42 @@ __global__ void finalize_frob_kernel(const long long* state, const long long* hs
             }
             fs_min = nb::u2f(hi);
         }
+        if (!mask_enabled) fs_min = -INFINITY;            // Filter(mask=False): every voxel passes (filtering.py:910-933)
         sp[NB200_SP_FROBSQ_MIN] = (double)fs_min;
+        if (fast) {
+            const double u = 5.9604644775390625e-08;
+            const double gmax = (double)nb::u2f((uint32_t)hstats[NB200_HS_MAX_G_BITS]);
+            const double delta = 40.0 * u * gmax * max_scale;
+            // the approximate provably-zero test needs ||H||_F <= 1.376 ||H~||_F: frob_sq~ >= 64 delta^2 (and a normal k * fs)
+            const double guard = fmax(64.0 * delta * delta, 1e-18);
+            double lo, hi;
+            if (fs_min != fs_min) { lo = INFINITY; hi = INFINITY; }          // NaN cut: nothing passes
+            else if (fs_min == -INFINITY) { lo = -INFINITY; hi = guard; }
+            else {
+                const double f = (double)fs_min, sq = sqrt(f);
+                const double e0 = 6.0 * delta * sq + 9.0 * delta * delta + 64.0 * u * f;
+                lo = f - 1.5 * e0;
+                hi = (delta <= sq / 8.0) ? fmax(f + 2.5 * e0, guard) : INFINITY;
+            }
+            sp[NB200_SP_FS_LO] = lo;
+            sp[NB200_SP_FS_HI] = hi;
+            sp[NB200_SP_ZT_C] = 2.5 * delta;
+            sp[NB200_SP_DELTA] = delta;
+        }
     }
+    sp[NB200_SP_AMBIG] = ambig;
     sp[NB200_SP_FROB_THR] = thr;
     sp[NB200_SP_FROB_CUT] = cut;
     sp[NB200_SP_SKIP] = any ? 0.0 : 1.0;
     sp[NB200_SP_STATUS] = status;
+}
+
+__global__ void finalize_frob_resolve_kernel(const long long* hstats, double* sp) {
+    if (threadIdx.x != 0 || sp[NB200_SP_AMBIG] == 0.0 || sp[NB200_SP_UNSAFE] != 0.0) return;
+    const float max_abs = (float)sp[NB200_SP_MAX_ABS];
+    const float top = sqrtf(nb::u2f((uint32_t)hstats[NB200_HS_MAX_FROBSQ_BITS])) / max_abs;
+    sp[NB200_SP_SKIP] = top > (float)sp[NB200_SP_FROB_CUT] ? 0.0 : 1.0;
+    sp[NB200_SP_AMBIG] = 0.0;
 }
 
 __global__ void finalize_label_kernel(const long long* state, int log_domain, double* out) {
@@ -516,8 +564,22 @@ int nb200_finalize_max_abs(const long long* hstats, double* sp, void* stream) {
 int nb200_finalize_frob(const long long* state, const long long* hstats, double fixed_thresh, double division,
                         double* sp, void* stream) {
     NB_REQUIRE(state && hstats && sp, NB200_ERR_ARG, "nb200_finalize_frob: null argument");
-    finalize_frob_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(state, hstats, fixed_thresh, division, sp);
+    finalize_frob_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(state, hstats, fixed_thresh, division, sp, 0, 0.0, 1);
     return nb::check_launch("finalize_frob");
+}
+
+int nb200_finalize_frob_fast(const long long* state, const long long* hstats, double fixed_thresh, double division,
+                             double max_scale, int mask_enabled, double* sp, void* stream) {
+    NB_REQUIRE(state && hstats && sp && max_scale >= 0.0, NB200_ERR_ARG, "nb200_finalize_frob_fast: bad argument");
+    finalize_frob_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(state, hstats, fixed_thresh, division, sp,
+                                                              max_scale > 0.0 ? 1 : 0, max_scale, mask_enabled);
+    return nb::check_launch("finalize_frob_fast");
+}
+
+int nb200_finalize_frob_resolve(const long long* hstats, double* sp, void* stream) {
+    NB_REQUIRE(hstats && sp, NB200_ERR_ARG, "nb200_finalize_frob_resolve: null argument");
+    finalize_frob_resolve_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(hstats, sp);
+    return nb::check_launch("finalize_frob_resolve");
 }
 
 int nb200_finalize_label_threshold(const long long* state, int log_domain, double* out, void* stream) {

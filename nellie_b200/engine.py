@@ -39,6 +39,7 @@ class FilterParams:
     truncate: float = 3.0
     remove_edges: bool = False
     sigmas: Optional[Sequence[float]] = None
+    mask: bool = True          # Filter._run_frame(mask=False): no Frobenius gate (filtering.py:910-933)
 
     def z_ratio(self) -> float:  # filtering.py:75-78
         z_res = self.dim_res.get("Z") or self.dim_res.get("X") or 1.0
@@ -191,6 +192,14 @@ class FrangiEngine3D:
         self.sparse_list = True  # sparse K3 as stream + solve kernels over a global candidate list (else: one kernel, smem queues)
         self.list_count = torch.zeros(1, dtype=torch.int64, device=dev)
         self.sparse_k3 = True  # K3 from K2's per-voxel record (nb200_frangi_sparse); False = dense march (nb200_frangi_accumulate)
+        # Fast Hessian path (hessian_fast.cu): approximate classification with proven margins + exact candidates in
+        # one barrier-free TMA march.  Needs nx % 4 == 0, a verified division mode and < 2^32 voxels per buffer;
+        # otherwise (and whenever the device flags sp[UNSAFE]) the exact kernels above run.
+        self.fast_path = (nx % 4 == 0 and self.div_mode in (_cabi.DIV_FAST, _cabi.DIV_POW2)
+                          and self.nz_buf * ny * nx < 2 ** 32 and ny >= 5 and nx >= 12)
+        self.fast_ws = torch.zeros(int(self.lib.nb200_hessian_fast_workspace_bytes()) // 4, dtype=torch.int32, device=dev)
+        self.max_scale = float(1.0 / (np.float64(self.fd[1::2].min()) ** 2))
+        self.diag = None      # set to a zeroed int64[8] device tensor to collect candidate / survivor counts (tests)
         self.fuse_yx = True   # Y and X blur passes in one kernel (nb200_gauss_yx); False = one kernel per axis
         self.launches = 0     # C-ABI calls
         self.kernels = 0      # CUDA kernels enqueued by those calls
@@ -229,7 +238,8 @@ class FrangiEngine3D:
     # CUDA kernels behind one C-ABI call (default 1): K2 = march + border shell, redo = reset + IEEE twin + shell,
     # sparse K3 = stream + solve, dense K3 = march + IEEE twin + shell, percentile = radix select passes
     KERNELS_PER_CALL = {"nb200_hessian_stats_code": 2, "nb200_hessian_stats_redo": 3, "nb200_frangi_sparse": 2,
-                        "nb200_frangi_accumulate": 3, "nb200_percentile": 17}
+                        "nb200_frangi_accumulate": 3, "nb200_percentile": 17, "nb200_hessian_stats_fast": 4,
+                        "nb200_hessian_stats_ambig": 2, "nb200_frangi_fast": 2, "nb200_frangi_sparse_gated": 2}
 
     def _call(self, name, *args):
         self.launches += 1
@@ -319,8 +329,14 @@ class FrangiEngine3D:
         self._call("nb200_lattice_sample", _ptr(g), C.byref(own), sz, sy, sx, _ptr(self.samples), st)
         self._histogram(self.samples, self.n_samples, _cabi.TF_NONE, None)
         self._call("nb200_finalize_gamma", _ptr(self.hist), _ptr(sp_i), st)
-        # F4: Hessian statistics (max|H|, max frob^2, frob samples) + K2's per-voxel record for the sparse K3
+        fixed = float("nan") if self.p.frob_thresh is None else float(self.p.frob_thresh)
+        division = float(self.p.frob_thresh_division or 0.0)
+        mask_on = 1 if self.p.mask else 0
         self._call("nb200_hstats_reset", _ptr(self.hstats), st)
+        if self.fast_path:
+            self._analyse_sigma_fast(i, g, own, sp_i, fixed, division, mask_on, st)
+            return
+        # F4: Hessian statistics (max|H|, max frob^2, frob samples) + K2's per-voxel record for the sparse K3
         code = self.code if self.sparse_k3 else None
         self._call("nb200_hessian_stats_code", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
                    sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), _ptr(code), st)
@@ -333,14 +349,12 @@ class FrangiEngine3D:
             self.reduce_hstats(self.hstats)
             self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
         # F5: Frobenius threshold
-        fixed = float("nan") if self.p.frob_thresh is None else float(self.p.frob_thresh)
-        division = float(self.p.frob_thresh_division or 0.0)
-        if self.p.frob_thresh is None and division != 0.0:
-            div_ptr = C.c_void_p(sp_i.data_ptr() + 8 * _cabi.SP_MAX_ABS)
-            self._histogram(self.samples, self.n_samples, _cabi.TF_DIV, div_ptr)
+        self._frob_histogram(sp_i, st)
+        if mask_on:
+            self._call("nb200_finalize_frob", _ptr(self.hist), _ptr(self.hstats), fixed, division, _ptr(sp_i), st)
         else:
-            self._call("nb200_hist_reset", _ptr(self.hist), st)
-        self._call("nb200_finalize_frob", _ptr(self.hist), _ptr(self.hstats), fixed, division, _ptr(sp_i), st)
+            self._call("nb200_finalize_frob_fast", _ptr(self.hist), _ptr(self.hstats), fixed, division, 0.0, 0,
+                       _ptr(sp_i), st)
         # F4-F9 fused
         if self.sparse_k3:
             # candidate list: the output volume is idle until finalize() and holds one word per owned voxel
@@ -351,6 +365,43 @@ class FrangiEngine3D:
         else:
             self._call("nb200_frangi_accumulate", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode,
                        float(self.p.alpha_sq), float(self.p.beta_sq), _ptr(sp_i), st)
+
+    def _frob_histogram(self, sp_i, st):
+        """Histogram of the frob samples / max|H| (filtering.py:407-444); nothing to do for a fixed threshold."""
+        division = float(self.p.frob_thresh_division or 0.0)
+        if self.p.mask and self.p.frob_thresh is None and division != 0.0:
+            div_ptr = C.c_void_p(sp_i.data_ptr() + 8 * _cabi.SP_MAX_ABS)
+            self._histogram(self.samples, self.n_samples, _cabi.TF_DIV, div_ptr)
+        else:
+            self._call("nb200_hist_reset", _ptr(self.hist), st)
+
+    def _analyse_sigma_fast(self, i, g, own, sp_i, fixed, division, mask_on, st):
+        """F4-F9 through hessian_fast.cu.  Every exact fallback is enqueued behind a device flag: the kernels return at
+        once unless the statistics pass raised sp[UNSAFE] (value range / exactness argument) or sp[AMBIG]."""
+        sz, sy, sx = self.strides
+        a_sq, b_sq = float(self.p.alpha_sq), float(self.p.beta_sq)
+        self._call("nb200_hessian_stats_fast", _ptr(g), C.byref(own), self._fd_c, self.div_mode, sz, sy, sx,
+                   _ptr(self.samples), _ptr(self.hstats), _ptr(self.fast_ws), st)
+        self.reduce_hstats(self.hstats)
+        self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
+        self._call("nb200_hessian_stats_redo", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
+                   sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), _ptr(self.code), st)
+        self.reduce_hstats(self.hstats)
+        self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
+        self._frob_histogram(sp_i, st)
+        self._call("nb200_finalize_frob_fast", _ptr(self.hist), _ptr(self.hstats), fixed, division, self.max_scale,
+                   mask_on, _ptr(sp_i), st)
+        if mask_on:
+            # emptiness of the mask undecided by the bounds (cut in [0.99, 3.01)): exact max frob^2, gated on sp[AMBIG]
+            self._call("nb200_hessian_stats_ambig", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
+                       sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), st)
+            self.reduce_hstats(self.hstats)
+            self._call("nb200_finalize_frob_resolve", _ptr(self.hstats), _ptr(sp_i), st)
+        self._call("nb200_frangi_fast", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode, a_sq, b_sq,
+                   _ptr(sp_i), _ptr(self.diag), st)
+        lst = self.out if self.sparse_list else None
+        self._call("nb200_frangi_sparse_gated", _ptr(g), _ptr(self.code), _ptr(self.acc), C.byref(own), self._fd_c,
+                   self.div_mode, a_sq, b_sq, _ptr(sp_i), _ptr(lst), self.out.numel(), _ptr(self.list_count), st)
 
     def run_sigmas(self):
         """filtering.py:814-851 for every sigma; leaves max-over-sigma / dead flags in ``acc``.

@@ -104,7 +104,7 @@ class FrangiEngine2D:
         """One 2-D frame.  A 2048^2 frame is ~180 small kernels (3 ms of GPU time, launch-bound), so from the third
         call on the whole per-frame sequence is replayed as ONE CUDA graph (captured on the second call, after an
         eager warm-up; all buffers are engine-owned and static, only the upload of the frame stays outside)."""
-        key = bool(apply_mask_volume)
+        key = (bool(apply_mask_volume), bool(getattr(self.p, "mask", True)))
         self.gauss[0].copy_(frame)
         if not self.use_graph:
             res = self._filter_frame(apply_mask_volume)
@@ -129,11 +129,11 @@ class FrangiEngine2D:
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                res = self._filter_frame(key)
+                res = self._filter_frame(key[0])
         except Exception:                       # capture is an optimisation: fall back to eager launches for good
             self.use_graph = False
             torch.cuda.synchronize(self.device)
-            return self._filter_frame(key)
+            return self._filter_frame(key[0])
         self._graph_calls[key] = self.launches - before
         self._graphs[key] = (graph, res)
         graph.replay()
@@ -166,7 +166,8 @@ class FrangiEngine2D:
                 self._histogram(self.n_samples, _cabi.TF_DIV, C.c_void_p(sp_i.data_ptr() + 8 * _cabi.SP_MAX_ABS))
             else:
                 self._call("nb200_hist_reset", _ptr(self.hist), st)
-            self._call("nb200_finalize_frob", _ptr(self.hist), _ptr(self.hstats), fixed, division, _ptr(sp_i), st)
+            self._call("nb200_finalize_frob_fast", _ptr(self.hist), _ptr(self.hstats), fixed, division, 0.0,
+                       1 if getattr(self.p, "mask", True) else 0, _ptr(sp_i), st)
             self._call("nb200_frangi_accumulate_2d", _ptr(g), _ptr(self.acc), self.ny, self.nx, self._fd_c,
                        float(self.p.beta_sq), _ptr(sp_i), st)
         # F10: LoG blobness on the sigma_max-blurred frame

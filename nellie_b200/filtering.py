@@ -164,11 +164,10 @@ class Filter:
     # ---- per-frame API (reference: filtering.py:910-967) ----------------------------------------
     def _run_frame(self, t, mask=True):
         """Vesselness of frame ``t`` BEFORE _mask_volume, as a host float32 array."""
-        if not mask:
-            raise NotImplementedError("mask=False (no Frobenius gating) is not implemented on the B200 path")
         logger.info("Running Frangi filter on t=%s.", t)
         frame_cpu = self.im_memmap[t, ...]
         eng = self._engine_for(frame_cpu.shape)
+        eng.p.mask = bool(mask)          # mask=False: every voxel passes the Frobenius gate (filtering.py:563-566)
         with torch.cuda.device(eng.device):
             out = eng.filter_frame(self._to_device(frame_cpu), apply_mask_volume=False)
             return out.cpu().numpy()
@@ -185,12 +184,14 @@ class Filter:
     def filter_frame_device(self, frame: torch.Tensor) -> torch.Tensor:
         """Device-resident fast path: one frame in, final ``im_preprocessed`` frame out (engine buffer)."""
         eng = self._engine_for(tuple(frame.shape))
+        eng.p.mask = True
         with torch.cuda.device(eng.device):
             return eng.filter_frame(frame, apply_mask_volume=True)
 
-    def filter_frame_host(self, frame_cpu) -> np.ndarray:
+    def filter_frame_host(self, frame_cpu, mask=True) -> np.ndarray:
         """Host array in, host array out: H2D, the whole per-frame path, D2H."""
         eng = self._engine_for(tuple(frame_cpu.shape))
+        eng.p.mask = bool(mask)
         with torch.cuda.device(eng.device):
             out = eng.filter_frame(self._to_device(frame_cpu), apply_mask_volume=True)
             return out.cpu().numpy()
@@ -199,12 +200,11 @@ class Filter:
     def _run_filter(self, mask=True):
         """T loop of filtering.py:1005-1031 as a pipelined frame stream (pipeline.py): the upload of frame
         t+1 and the download + memmap write of frame t-1 overlap the kernels of frame t."""
-        if not mask:
-            raise NotImplementedError("mask=False is not implemented on the B200 path")
         from .pipeline import FramePipeline
         single = bool(self.im_info.no_t) or self.num_t == 1
         frame_shape = tuple(self.im_memmap.shape[1:])          # the reference indexes im_memmap[t, ...] (T always present)
         eng = self._engine_for(frame_shape)
+        eng.p.mask = bool(mask)
 
         def get_in(t):
             return self.im_memmap[t, ...]

@@ -54,7 +54,7 @@ def _recording_filter(Filter):
     return Rec
 
 
-def run_reference(raw, dim_res, no_z, filter_kwargs=None, label_kwargs=None, sigmas=None):
+def run_reference(raw, dim_res, no_z, filter_kwargs=None, label_kwargs=None, sigmas=None, run_mask=True):
     Filter, Label = ref_shim.load()
     Rec = _recording_filter(Filter)
     info = ref_shim.im_info_for(raw.shape, dim_res, no_z)
@@ -65,7 +65,7 @@ def run_reference(raw, dim_res, no_z, filter_kwargs=None, label_kwargs=None, sig
         f.sigmas = [float(s) for s in sigmas]
         f.halo = f._compute_halo()
     f.im_memmap = raw[None].copy()  # the reference mutates float32 inputs
-    pre = f._run_frame(0)
+    pre = f._run_frame(0) if run_mask else f._run_frame(0, mask=False)
     pre = np.array(pre, copy=True)
     fin = f._mask_volume(pre.copy()) if float(np.sum(pre)) > 0.0 else pre.copy()
     lab = Label(info, device="cpu", **(label_kwargs or {}))
@@ -88,7 +88,8 @@ def save_case(name, raw, dim_res, no_z, **kw):
     out = run_reference(raw, dim_res, no_z, **kw)
     meta = dict(dim_res=dim_res, no_z=bool(no_z),
                 filter_kwargs=kw.get("filter_kwargs") or {}, label_kwargs=kw.get("label_kwargs") or {},
-                explicit_sigmas=None if kw.get("sigmas") is None else [float(s) for s in kw["sigmas"]])
+                explicit_sigmas=None if kw.get("sigmas") is None else [float(s) for s in kw["sigmas"]],
+                run_mask=bool(kw.get("run_mask", True)))
     path = os.path.join(GOLDEN_DIR, f"{name}.npz")
     np.savez_compressed(path, raw=raw, meta=np.asarray(json.dumps(meta)), **out)
     nz = int((out["frangi"] > 0).sum())
@@ -145,6 +146,18 @@ def main():
     big = tubular_phantom_np((40, 128, 200), seed=24, n_tubes=30)
     big8 = np.clip(np.round(big / 2.0), 0, 255).astype(np.uint8)
     save_case("phantom3d_strided", big8, iso, False, sigmas=[1.0, 1.6])
+    # (6) power-of-two pixel size (BASELINE config #2: dim_res 0.125, radii 0.25 .. 0.675 um -> sigmas 1.0 .. 1.6):
+    #     every finite-difference divisor is a power of two (division mode POW2 of the CUDA kernels)
+    p2 = {"X": 0.125, "Y": 0.125, "Z": 0.125, "T": 1.0}
+    save_case("phantom3d_pow2", tubular_phantom_np((32, 64, 72), seed=25, n_tubes=7), p2, False,
+              filter_kwargs={"min_radius_um": 0.25, "max_radius_um": 0.675})
+    # (7) BASELINE config #3 in small: isotropic 0.1 um, the bench's explicit six sigmas, > 1.2e6 voxels (lattice
+    #     strides > 1, Z radii 3-4); stored as uint8 like (5)
+    c3 = tubular_phantom_np((48, 160, 160), seed=26, n_tubes=40)
+    c3 = np.clip(np.round(c3 / 2.0), 0, 255).astype(np.uint8)
+    save_case("phantom3d_cfg3", c3, iso, False, sigmas=[1.0, 1.4, 1.8, 2.2, 2.6, 3.0])
+    # (8) Filter._run_frame(t, mask=False) (filtering.py:910-933): no Frobenius gate
+    save_case("phantom3d_nomask", tubular_phantom_np((20, 40, 48), seed=27, n_tubes=4), iso, False, run_mask=False)
     label_only_cases()
 
 

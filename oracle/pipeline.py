@@ -46,6 +46,7 @@ class FrameSpec:
     truncate: float = 3.0
     remove_edges: bool = False
     sigmas: Optional[Sequence[float]] = None  # explicit override (BASELINE config #3)
+    run_mask: bool = True  # Filter._run_frame(t, mask=...) (filtering.py:910): False = no Frobenius gate
     # Label knobs
     label_min_radius_um: float = 0.25
     threshold_sampling_pixels: int = 1_000_000
@@ -361,6 +362,8 @@ def frangi_frame(frame, spec: FrameSpec, trace: Optional[list] = None):
         gamma_sq = 2.0 * (float(gamma) ** 2)
         comp, frob_sq, max_abs, frob = hessian(gauss, spec)
         m, thr = frob_mask(frob, spec)
+        if not spec.run_mask:                 # filtering.py:563-566: h_mask = ones when mask=False
+            m = np.ones_like(gauss, dtype=bool)
         rec = None
         if trace is not None:
             rec = dict(sigma=s, gauss=gauss.copy(), gamma=gamma, gamma_sq=gamma_sq, max_abs=max_abs,

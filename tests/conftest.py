@@ -26,7 +26,8 @@ def load_golden(name):
 def spec_from_meta(meta):
     from oracle.pipeline import FrameSpec
     fk = meta.get("filter_kwargs") or {}
-    return FrameSpec(dim_res=meta["dim_res"], no_z=meta["no_z"], sigmas=meta.get("explicit_sigmas"), **fk)
+    return FrameSpec(dim_res=meta["dim_res"], no_z=meta["no_z"], sigmas=meta.get("explicit_sigmas"),
+                     run_mask=bool(meta.get("run_mask", True)), **fk)
 
 
 @pytest.fixture(scope="session")

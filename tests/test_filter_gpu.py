@@ -8,7 +8,8 @@ from conftest import load_golden, spec_from_meta
 
 pytestmark = pytest.mark.gpu
 
-CASES_3D = ["sample_crop", "phantom3d_iso", "phantom3d_aniso", "phantom3d_strided"]
+CASES_3D = ["sample_crop", "phantom3d_iso", "phantom3d_aniso", "phantom3d_strided", "phantom3d_pow2", "phantom3d_cfg3",
+            "phantom3d_nomask"]
 
 
 def _filter_for(g, **kw):
@@ -34,13 +35,15 @@ def test_filter_3d_matches_reference(name):
     g = load_golden(name)
     f = _filter_for(g)
     raw_before = g["raw"].copy()
-    pre = f._run_frame(0)
+    run_mask = bool(g["meta"].get("run_mask", True))
+    pre = f._run_frame(0, mask=run_mask)
     rec = f._engine.sigma_records()
     assert np.array_equal(g["raw"], raw_before), "input frame was mutated"
     assert np.allclose(f.sigmas, g["sigmas"], rtol=0, atol=0)
     # per-sigma scalars derived on the device
     assert rec[:, 0].tolist() == g["gamma"].tolist(), "gamma differs"
-    assert rec[:, 2].tolist() == g["frob_thr"].tolist(), "frobenius threshold differs"
+    if run_mask:
+        assert rec[:, 2].tolist() == g["frob_thr"].tolist(), "frobenius threshold differs"
     assert pre.dtype == np.float32 and pre.shape == g["frangi_pre"].shape
     ok = frangi_tolerance(pre, g["frangi_pre"])
     assert ok.all(), f"{(~ok).sum()} voxels outside tolerance"
@@ -50,8 +53,11 @@ def test_filter_3d_matches_reference(name):
     fin = f._mask_volume(pre)
     assert np.array_equal(fin > 0, g["frangi"] > 0)
     assert frangi_tolerance(fin, g["frangi"]).all()
+    # the golden files were produced by the reference itself: the stated bar is the tolerance above, the observed
+    # result is bit-identity — keep it that way
+    assert nbad == 0 and np.array_equal(fin, g["frangi"])
     # fused path (device resident percentile + opening)
-    fin2 = f.filter_frame_host(g["raw"])
+    fin2 = f.filter_frame_host(g["raw"], mask=run_mask)
     assert np.array_equal(fin2, fin)
 
 

@@ -46,8 +46,8 @@ def test_gaussian_cascade_is_bit_exact(name):
     assert np.array_equal(got, trace[0]["gauss"])
 
 
-@pytest.mark.parametrize("name", ["sample_crop", "phantom3d_iso", "phantom3d_aniso", "phantom3d_strided"])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name", ["sample_crop", "phantom3d_iso", "phantom3d_aniso", "phantom3d_strided", "phantom3d_pow2"])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_hessian_components_and_frob_samples_are_bit_exact(name, mode):
     import torch
     from nellie_b200 import _cabi
@@ -55,6 +55,8 @@ def test_hessian_components_and_frob_samples_are_bit_exact(name, mode):
     g, spec, trace, eng, st = _setup(name)
     if mode == 1 and eng.div_mode == 0:
         pytest.skip("fast division not verified for these spacings")
+    if mode == 2 and eng.div_mode != 2:
+        pytest.skip("spacings are not powers of two")
     for rec in (trace[0], trace[-1]):
         gauss = torch.from_numpy(rec["gauss"]).cuda()
         out6 = torch.zeros((6,) + rec["gauss"].shape, dtype=torch.float32, device="cuda")
@@ -76,6 +78,20 @@ def test_hessian_components_and_frob_samples_are_bit_exact(name, mode):
         ref = np.sqrt(frob_sq)[::sz, ::sy, ::sx]
         got_s = eng.samples.cpu().numpy()[:ref.size].reshape(ref.shape)
         assert np.array_equal(got_s, ref), int((got_s != ref).sum())
+        # the fast statistics pass (approximate march + exact re-evaluation of the near-maximum sub-chunks)
+        if mode in (1, 2) and eng.fast_path:
+            eng.samples.zero_()
+            _cabi.call("nb200_hstats_reset", _vp(eng.hstats), st)
+            _cabi.call("nb200_hessian_stats_fast", _vp(gauss), C.byref(own), eng._fd_c, mode, sz, sy, sx,
+                       _vp(eng.samples), _vp(eng.hstats), _vp(eng.fast_ws), st)
+            hs = eng.hstats.cpu().numpy()
+            assert hs[_cabi.HS_FALLBACK] == 0
+            assert np.array([hs[0]], dtype=np.uint32).view(np.float32)[0] == np.float32(max_abs)
+            approx = np.array([hs[_cabi.HS_APPROX_MAX_BITS]], dtype=np.uint32).view(np.float32)[0]
+            assert abs(approx - max_abs) <= 1e-4 * max_abs
+            assert np.array([hs[3]], dtype=np.uint32).view(np.float32)[0] == np.abs(rec["gauss"]).max()
+            got_s = eng.samples.cpu().numpy()[:ref.size].reshape(ref.shape)
+            assert np.array_equal(got_s, ref), int((got_s != ref).sum())
 
 
 def test_divisor_modes():
