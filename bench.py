@@ -245,7 +245,8 @@ def run_b200_arm(args):
     # per-sigma average launch time of the per-sigma kernels (calls come in sigma order, once per sigma and step)
     per_sigma = {}
     nsig = len(SIGMAS_CFG3)
-    for name in ("nb200_gauss_axis", "nb200_gauss_yx", "nb200_hessian_stats_code", "nb200_frangi_sparse", "nb200_frangi_accumulate"):
+    for name in ("nb200_gauss_axis", "nb200_gauss_yx", "nb200_hessian_stats_code", "nb200_frangi_sparse", "nb200_frangi_accumulate",
+                 "nb200_hessian_stats_fast", "nb200_frangi_fast"):
         evs = [(a, b) for nm, a, b in (eng.profile or []) if nm == name]
         if evs and len(evs) % nsig == 0:
             per_sigma[name] = [round(float(np.mean([a.elapsed_time(b) for a, b in evs[i::nsig]])), 3) for i in range(nsig)]
@@ -300,6 +301,8 @@ def run_b200_arm(args):
            "nb200_hessian_stats_code": (8.0, "K2 march_kernel<StatsEpi>: dense Hessian, max|H|, frob samples, per-voxel record (R gauss 4 + W code 4)"),
            "nb200_frangi_sparse": (12.0, "K3 sparse_stream + sparse_solve: mask + eigenvalues + vesselness + max/AND (R code 4 + R acc 4 + W acc 4)"),
            "nb200_frangi_accumulate": (12.0, "K3 march_kernel<FrangiEpi> (dense form)"),
+           "nb200_hessian_stats_fast": (4.0, "K2 stats_fast_kernel + fixup + shell: max|H|, frob samples, value range (R gauss 4)"),
+           "nb200_frangi_fast": (12.0, "K3 frangi_fast_kernel + shell: mask + eigenvalues + vesselness + max/AND (R gauss 4 + R acc 4 + W acc 4)"),
            "nb200_finalize_opening": (8.0, "K5 opening_march: percentile mask + binary opening (R 4 + W 4)")}
     # DRAM bytes per launch from the ncu --set full captures under profiles/ (1024^3, one GPU): read + write
     # (profiles/r1e_ncu_full_1024.md; K3 = stream + solve of the sigma-1.4 launch, the sigma-1.0 launch moves 36.7e9)

@@ -175,16 +175,22 @@ def test_pipeline_with_pinned_buffers():
 
 @pytest.mark.parametrize("name", CASES_3D)
 def test_sparse_k3_equals_dense_march(name):
-    """nb200_frangi_sparse (K3 from K2's per-voxel record, queues of candidates) against the dense marching
-    K3 (nb200_frangi_accumulate) and the per-axis blur kernels: every variant must give the same bits."""
+    """The fast path (nb200_hessian_stats_fast + nb200_frangi_fast), nb200_frangi_sparse (K3 from K2's per-voxel
+    record, queues of candidates), the dense marching K3 (nb200_frangi_accumulate) and the per-axis blur kernels:
+    every variant must give the same bits."""
     import torch
     g = load_golden(name)
     f = _filter_for(g)
     eng = f._engine_for(g["raw"].shape)
     frame = torch.from_numpy(g["raw"].astype(np.float32)).cuda()
-    assert eng.sparse_k3 and eng.fuse_yx
+    eng.p.mask = bool(g["meta"].get("run_mask", True))
+    assert eng.sparse_k3 and eng.fuse_yx and eng.fast_path
+    a0 = eng.filter_frame(frame, apply_mask_volume=False).clone()      # fast path (hessian_fast.cu)
+    acc_0 = eng.acc.clone()
+    eng.fast_path = False                                              # exact K2 record + sparse K3 (stream + solve)
     a = eng.filter_frame(frame, apply_mask_volume=False).clone()
     acc_a = eng.acc.clone()
+    assert torch.equal(a0, a) and torch.equal(acc_0, acc_a), int((acc_0 != acc_a).sum())
     eng.overlap_blur = True                      # blur of sigma i+1 on a side stream under K2/K3 of sigma i
     a1 = eng.filter_frame(frame, apply_mask_volume=False).clone()
     assert torch.equal(a, a1) and torch.equal(acc_a, eng.acc)

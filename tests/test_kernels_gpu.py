@@ -87,8 +87,11 @@ def test_hessian_components_and_frob_samples_are_bit_exact(name, mode):
             hs = eng.hstats.cpu().numpy()
             assert hs[_cabi.HS_FALLBACK] == 0
             assert np.array([hs[0]], dtype=np.uint32).view(np.float32)[0] == np.float32(max_abs)
+            # the approximate maximum covers the interior of the march only (the shell is evaluated exactly)
             approx = np.array([hs[_cabi.HS_APPROX_MAX_BITS]], dtype=np.uint32).view(np.float32)[0]
-            assert abs(approx - max_abs) <= 1e-4 * max_abs
+            nx = rec["gauss"].shape[2]
+            inner = max(float(np.abs(c[2:-2, 2:-2, 4:4 * ((nx - 2) // 4)]).max()) for c in rec["comp"].values())
+            assert abs(approx - inner) <= 1e-4 * inner, (approx, inner)
             assert np.array([hs[3]], dtype=np.uint32).view(np.float32)[0] == np.abs(rec["gauss"]).max()
             got_s = eng.samples.cpu().numpy()[:ref.size].reshape(ref.shape)
             assert np.array_equal(got_s, ref), int((got_s != ref).sum())
