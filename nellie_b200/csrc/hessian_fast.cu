@@ -40,17 +40,24 @@
 #include "hessian_march.cuh"
 #include "march_host.cuh"
 
-#ifndef NB200_STATS_REGS
-#define NB200_STATS_REGS 96
+#ifndef NB200_MARCH_UNROLL
+#define NB200_MARCH_UNROLL 1
+#endif
+#ifndef NB200_SLEEP_PRODUCER
+#define NB200_SLEEP_PRODUCER 20000
+#endif
+#ifndef NB200_SLEEP_CONSUMER
+#define NB200_SLEEP_CONSUMER 4000
 #endif
 
 namespace {
 namespace hf {
 
-constexpr int TX = hm::TX, RW = 2, NW = 7, NT = NW * 32, TYO = NW * RW, GR = TYO + 4, PITCH = hm::PITCH;
-constexpr int SLOT = hm::G_SLOT;
-static_assert(TYO == hm::TYO && GR == hm::GR && PITCH == TX + 8, "tile must match the TMA box of make_plane_map");
+constexpr int TX = 128, RW = 2, NW = 8, NT = NW * 32, TYO = NW * RW, GR = TYO + 4, PITCH = TX + 8;
+constexpr int SLOT = GR * PITCH;        // 136 x 20 floats = 10880 bytes: a multiple of 128, so every slot is TMA-aligned
+static_assert((SLOT * 4) % 128 == 0, "ring slots must stay 128-byte aligned");
 constexpr unsigned BOX_BYTES = GR * PITCH * 4;
+constexpr int MARCH_UNROLL = NB200_MARCH_UNROLL;
 constexpr int ZR = 32;                  // planes per max|H| record of the statistics pass
 constexpr unsigned WL_CAP = 16384;      // work-list entries (8 words each)
 constexpr int WL_HDR = 8;
@@ -66,46 +73,26 @@ struct Consts {
 template <int D>
 struct Ring {
     float g[D][SLOT];                   // TMA destinations, 128-byte aligned
-    unsigned long long full[D], empty[D];
+    unsigned long long full[D];         // "plane landed" mbarriers (TMA complete_tx)
+    unsigned released[D];               // warps that no longer need the plane in this slot
 };
 
-// ---- mbarrier helpers (bounded spin: a protocol bug traps instead of hanging the GPU) ----------------------------
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hm::smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    const unsigned a = hm::smem_u32(bar);
-    for (unsigned it = 0;; ++it) {
-        unsigned ok;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(a), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (it > (1u << 22)) __trap();
-    }
-}
-
-// the same on precomputed shared-window addresses (no generic->shared conversion inside the loop)
-__device__ __forceinline__ void mbar_arrive_a(unsigned a) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-}
+// ---- mbarrier / TMA helpers on shared-window addresses (bounded wait: a protocol bug traps instead of hanging) ------
+// A try_wait without a time hint returns almost at once on this part when the phase is not complete: the bare poll loops
+// issued 22 % of all instructions of the K3 kernel (ncu: 1 active thread in the producer's loop), and NANOSLEEP 200
+// between polls slept only ~20 ns.  The suspend-time hint (NS, nanoseconds) parks the thread in hardware instead.
+template <int NS>
 __device__ __forceinline__ void mbar_wait_a(unsigned a, unsigned parity) {
     for (unsigned it = 0;; ++it) {
         unsigned ok;
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(ok)
-            : "r"(a), "r"(parity)
+            : "r"(a), "r"(parity), "r"((unsigned)NS)       // suspend-time hint in ns: the hardware parks the thread
             : "memory");
         if (ok) return;
         if (it > (1u << 22)) __trap();
@@ -221,48 +208,57 @@ struct StepCtx {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// The march over global planes [zs, ze) (all interior).  D = ring depth, K = planes a released slot lags behind
-// (the epilogue may still read planes o-2-K .. o+2 during step o), L = extra slack before a slot is refilled.
+// The march over global planes [zs, ze) (all interior).  D = ring depth (power of two), K = planes a released slot
+// lags behind (the epilogue may still read planes o-2-K .. o+2 during step o).
+// Warp NW (the eighth) is the producer: one lane issues plane p as soon as its slot is free.  Warps 0..NW-1 consume.
 // Epi provides: prefetch(o), track(V4) [range of staged values], put<C>(row, V4) [second difference C of a row, as
 // soon as it is known], step(ctx) [end of the plane], finish().
+// The loop is deliberately NOT unrolled over the ring: the unrolled form (immediate shared-memory offsets) was 245 KB
+// of code for K3 and ran 30x slower — stall_no_instruction, the 32 KB instruction cache thrashed by divergent warps.
 // ------------------------------------------------------------------------------------------------------------------
-template <int D, int K, int L, class Epi>
-__device__ __forceinline__ void march(Ring<D>& rg, const CUtensorMap* map, const Geo& q, int zs, int ze, Epi& epi) {
-    constexpr int LEAD = D - 1 - K - L;          // plane i + LEAD is issued at the start of step i
-    static_assert(LEAD >= 5 && LEAD <= D - 1, "ring too shallow");
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_out = ze - zs, n_pl = n_out + 4;
-    const int off0 = (RW * warp + 2) * PITCH + 4 + 4 * lane;
-    const float* ring = &rg.g[0][0];
+// Ring protocol.  full[slot] is an mbarrier completed by the TMA transaction bytes of the plane.  There is no "empty"
+// barrier and no producer warp: every warp counts itself off a plane in released[slot] (shared-memory atomic), and the
+// warp that completes the count issues the TMA of the next plane for that slot at once.  (A dedicated producer lane
+// polling an empty-mbarrier issued 14 % of the kernel's instructions, and the eighth warp slot of the CTA was wasted.)
+template <int D>
+__device__ __forceinline__ void ring_init(Ring<D>& rg, const CUtensorMap* map, const Geo& q, int zs, int ze) {
+    static_assert((D & (D - 1)) == 0, "ring depth must be a power of two");
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             hm::mbar_init(&rg.full[k], 1);
-            hm::mbar_init(&rg.empty[k], NW);
+            rg.released[k] = 0u;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // first D planes: their slots are free
+        const int n_pl = ze - zs + 4;
+        const unsigned sb = hm::smem_u32(&rg);
+        const unsigned sb_full = sb + (unsigned)(sizeof(float) * D * SLOT);
+        for (int p = 0; p < D && p < n_pl; ++p)
+            tma_plane_a(sb + (unsigned)p * (unsigned)(SLOT * 4), map, sb_full + 8u * (unsigned)p, q.x0 - 4, q.y0 - 2,
+                        zs - 2 - q.v.zg_off + p);
     }
     __syncthreads();                              // the only CTA-wide barrier of the kernel
-    const int zb0 = zs - 2 - q.v.zg_off;          // buffer plane of relative plane 0
-    const unsigned sb = hm::smem_u32(&rg);        // shared-window address of the ring
-    const unsigned sb_full = sb + (unsigned)(sizeof(float) * D * SLOT), sb_empty = sb_full + 8u * D;
-    const int tx0 = q.x0 - 4, ty0 = q.y0 - 2;
-    auto issue = [&](int p, int slot) {           // one lane
-        tma_plane_a(sb + (unsigned)slot * (unsigned)(SLOT * 4), map, sb_full + 8u * (unsigned)slot, tx0, ty0, zb0 + p);
-    };
-    // prologue: planes 0 .. LEAD-1 go to their first-use slots
-    if (lane == 0) {
-        for (int p = warp; p < LEAD && p < n_pl; p += NW) issue(p, p);
-    }
-    // Steps are unrolled D times: inside one unrolled copy the ring slots of all planes, the owner test of the
-    // producer duty (NW == D) and the barrier addresses are compile-time constants, so every shared-memory access
-    // carries an immediate offset and the carried first differences rotate through registers without copies.
-    auto wait_full = [&](int slot, int round) { mbar_wait_a(sb_full + 8u * (unsigned)slot, (unsigned)round & 1u); };
-    V4 a0[RW], a1[RW], dyP[RW], dxP[RW];
+}
+
+template <int D, int K, class Epi>
+__device__ __forceinline__ void consume(Ring<D>& rg, const CUtensorMap* map, const Geo& q, int zs, int ze, Epi& epi) {
+    static_assert(D >= 6 + K, "ring too shallow");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_out = ze - zs, n_pl = n_out + 4;
+    const int tx0 = q.x0 - 4, ty0 = q.y0 - 2, zb0 = zs - 2 - q.v.zg_off;
+    const int off0 = (RW * warp + 2) * PITCH + 4 + 4 * lane;
+    const float* ring = &rg.g[0][0];
+    const unsigned sb = hm::smem_u32(&rg);
+    const unsigned sb_full = sb + (unsigned)(sizeof(float) * D * SLOT);
+    auto wait_full = [&](int p) { mbar_wait_a<NB200_SLEEP_CONSUMER>(sb_full + 8u * ((unsigned)p & (D - 1)), (unsigned)(p / D) & 1u); };
+    V4 a0[RW], a1[RW], dyP[RW], dxP[RW], dyQ[RW], dxQ[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r) { dyQ[r] = V4(); dxQ[r] = V4(); }
     {
         // carries of the first step: a_o, a_{o+1}, first differences of plane o-1 (planes 0..3 sit in slots 0..3)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) wait_full(j, 0);
+        for (int j = 0; j < 4; ++j) wait_full(j);
         const float* Q0 = ring + off0;
         const float* Q1 = ring + SLOT + off0;
         const float* Q2 = ring + 2 * SLOT + off0;
@@ -279,92 +275,105 @@ __device__ __forceinline__ void march(Ring<D>& rg, const CUtensorMap* map, const
             dxP[r] = dxrow(f1, Q1[r * PITCH - 1], Q1[r * PITCH + 4]);
         }
     }
-    int owner = LEAD % NW;                        // warp that issues plane i + LEAD (kept incrementally when NW != D)
     const float* base = ring + off0;
-    for (int i0 = 0, round = 0; i0 < n_out; i0 += D, ++round) {
+#pragma unroll MARCH_UNROLL
+    for (int i = 0; i < n_out; ++i) {
+        epi.prefetch(zs + i);
+        StepCtx cx;
+        cx.ring = ring;
+        cx.off0 = off0;
+        cx.o = zs + i;
 #pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const int i = i0 + j;
-            if (i >= n_out) break;
-            // ---- producer duty: plane i + LEAD into slot (j + LEAD) % D ----
-            {
-                constexpr int dummy = 0; (void)dummy;
-                const int pslot = (j + LEAD) % D;
-                const int pround = round + (j + LEAD) / D;
-                const int pi = i + LEAD;
-                const bool mine = (NW == D) ? (warp == pslot) : (warp == owner);
-                if (mine && lane == 0 && pi < n_pl) {
-                    if (pround >= 1) mbar_wait_a(sb_empty + 8u * (unsigned)pslot, (unsigned)(pround - 1) & 1u);
-                    issue(pi, pslot);
-                }
-                if (NW != D) { if (++owner == NW) owner = 0; }
-            }
-            epi.prefetch(zs + i);
-            StepCtx cx;
-            cx.ring = ring;
-            cx.off0 = off0;
-            cx.o = zs + i;
-#pragma unroll
-            for (int t = 0; t < 5; ++t) cx.sl[t] = (j + t) % D;
-            wait_full((j + 4) % D, round + (j + 4) / D);       // plane i+4
-            const float* P0 = base + ((j + 2) % D) * SLOT;     // plane o
-            const float* P1 = base + ((j + 3) % D) * SLOT;     // plane o+1
-            const float* P2 = base + ((j + 4) % D) * SLOT;     // plane o+2
-            // ---- plane o: rows -2 .. 3 ----
-            const V4 m2 = ld4(P0 - 2 * PITCH), m1 = ld4(P0 - PITCH), r0 = ld4(P0), r1 = ld4(P0 + PITCH);
-            const V4 p1 = ld4(P0 + 2 * PITCH), p2 = ld4(P0 + 3 * PITCH);
-            const V4 dym = sub(r0, m2), dy0 = sub(r1, m1), dy1 = sub(p1, r0), dy2 = sub(p2, r1);
-            epi.template put<3>(0, sub(dy1, dym));
-            epi.template put<3>(1, sub(dy2, dy0));
-            const float2 L0 = ld2(P0 - 2), R0 = ld2(P0 + 4), L1 = ld2(P0 + PITCH - 2), R1 = ld2(P0 + PITCH + 4);
-            const V4 dxm = dxrow(m1, P0[-PITCH - 1], P0[-PITCH + 4]);
-            const V4 dx0 = dxrow(r0, L0.y, R0.x), dx1 = dxrow(r1, L1.y, R1.x);
-            const V4 dx2 = dxrow(p1, P0[2 * PITCH - 1], P0[2 * PITCH + 4]);
-            epi.template put<4>(0, sub(dx1, dxm));
-            epi.template put<4>(1, sub(dx2, dx0));
-            {
-                const float2 eA = sub2(r0.lo, L0), eB = sub2(r0.hi, r0.lo), eC = sub2(R0, r0.hi);
-                V4 xx;
-                xx.lo = sub2(eB, eA);
-                xx.hi = sub2(eC, eB);
-                epi.template put<5>(0, xx);
-            }
-            {
-                const float2 eA = sub2(r1.lo, L1), eB = sub2(r1.hi, r1.lo), eC = sub2(R1, r1.hi);
-                V4 xx;
-                xx.lo = sub2(eB, eA);
-                xx.hi = sub2(eC, eB);
-                epi.template put<5>(1, xx);
-            }
-            // ---- plane o+2: own rows (zz through a_p = g(p) - g(p-2)) ----
-            {
-                const V4 t0 = ld4(P2), t1 = ld4(P2 + PITCH);
-                epi.track(t0);
-                epi.track(t1);
-                const V4 a20 = sub(t0, r0), a21 = sub(t1, r1);
-                epi.template put<0>(0, sub(a20, a0[0]));
-                epi.template put<0>(1, sub(a21, a0[1]));
-                a0[0] = a1[0]; a0[1] = a1[1];
-                a1[0] = a20;   a1[1] = a21;
-            }
+        for (int t = 0; t < 5; ++t) cx.sl[t] = (i + t) & (D - 1);
+        wait_full(i + 4);
+        const float* P0 = base + cx.sl[2] * SLOT;     // plane o
+        const float* P1 = base + cx.sl[3] * SLOT;     // plane o+1
+        const float* P2 = base + cx.sl[4] * SLOT;     // plane o+2
+        // ---- plane o: rows -2 .. 3 ----
+        const V4 m2 = ld4(P0 - 2 * PITCH), m1 = ld4(P0 - PITCH), r0 = ld4(P0), r1 = ld4(P0 + PITCH);
+        const V4 p1 = ld4(P0 + 2 * PITCH), p2 = ld4(P0 + 3 * PITCH);
+        const V4 dym = sub(r0, m2), dy0 = sub(r1, m1), dy1 = sub(p1, r0), dy2 = sub(p2, r1);
+        epi.template put<3>(0, sub(dy1, dym));
+        epi.template put<3>(1, sub(dy2, dy0));
+        const float2 L0 = ld2(P0 - 2), R0 = ld2(P0 + 4), L1 = ld2(P0 + PITCH - 2), R1 = ld2(P0 + PITCH + 4);
+        const V4 dxm = dxrow(m1, P0[-PITCH - 1], P0[-PITCH + 4]);
+        const V4 dx0 = dxrow(r0, L0.y, R0.x), dx1 = dxrow(r1, L1.y, R1.x);
+        const V4 dx2 = dxrow(p1, P0[2 * PITCH - 1], P0[2 * PITCH + 4]);
+        epi.template put<4>(0, sub(dx1, dxm));
+        epi.template put<4>(1, sub(dx2, dx0));
+        {
+            const float2 eA = sub2(r0.lo, L0), eB = sub2(r0.hi, r0.lo), eC = sub2(R0, r0.hi);
+            V4 xx;
+            xx.lo = sub2(eB, eA);
+            xx.hi = sub2(eC, eB);
+            epi.template put<5>(0, xx);
+        }
+        {
+            const float2 eA = sub2(r1.lo, L1), eB = sub2(r1.hi, r1.lo), eC = sub2(R1, r1.hi);
+            V4 xx;
+            xx.lo = sub2(eB, eA);
+            xx.hi = sub2(eC, eB);
+            epi.template put<5>(1, xx);
+        }
+        // ---- plane o+2: own rows (zz through a_p = g(p) - g(p-2)) ----
+        {
+            const V4 t0 = ld4(P2), t1 = ld4(P2 + PITCH);
+            epi.track(t0);
+            epi.track(t1);
+            const V4 a20 = sub(t0, r0), a21 = sub(t1, r1);
+            epi.template put<0>(0, sub(a20, a0[0]));
+            epi.template put<0>(1, sub(a21, a0[1]));
+            a0[0] = a1[0]; a0[1] = a1[1];
+            a1[0] = a20;   a1[1] = a21;
+        }
+        if (!Epi::kLagZ) {
             // ---- plane o+1: first differences of the own rows; mixed Z derivatives against the carried plane o-1 ----
-            {
+            const V4 qm = ld4(P1 - PITCH), q0 = ld4(P1), q1 = ld4(P1 + PITCH), qp = ld4(P1 + 2 * PITCH);
+            if (i == n_out - 1) { epi.track(qm); epi.track(qp); }   // plane above the chunk: rows owned by nobody else
+            const V4 dyN0 = sub(q1, qm), dyN1 = sub(qp, q0);
+            const V4 dxN0 = dxrow(q0, P1[-1], P1[4]), dxN1 = dxrow(q1, P1[PITCH - 1], P1[PITCH + 4]);
+            epi.template put<1>(0, sub(dyN0, dyP[0]));
+            epi.template put<1>(1, sub(dyN1, dyP[1]));
+            epi.template put<2>(0, sub(dxN0, dxP[0]));
+            epi.template put<2>(1, sub(dxN1, dxP[1]));
+            dyP[0] = dy0; dyP[1] = dy1;
+            dxP[0] = dx0; dxP[1] = dx1;
+        } else {
+            // ---- lagged form (epilogues that take every component on its own, i.e. the statistics): the mixed Z
+            //      derivatives of plane o-1 from the first differences of planes o (just computed) and o-2 (carried).
+            //      No load from plane o+1: a third of the shared-memory wavefronts of the step. ----
+            if (i > 0) {
+                epi.template put<1>(0, sub(dy0, dyQ[0]));
+                epi.template put<1>(1, sub(dy1, dyQ[1]));
+                epi.template put<2>(0, sub(dx0, dxQ[0]));
+                epi.template put<2>(1, sub(dx1, dxQ[1]));
+            }
+            dyQ[0] = dyP[0]; dyQ[1] = dyP[1]; dxQ[0] = dxP[0]; dxQ[1] = dxP[1];
+            dyP[0] = dy0; dyP[1] = dy1; dxP[0] = dx0; dxP[1] = dx1;
+            if (i == n_out - 1) {                           // last plane of the chunk: its own mixed derivatives now
                 const V4 qm = ld4(P1 - PITCH), q0 = ld4(P1), q1 = ld4(P1 + PITCH), qp = ld4(P1 + 2 * PITCH);
-                if (i == n_out - 1) { epi.track(qm); epi.track(qp); }   // plane above the chunk: rows owned by nobody else
+                epi.track(qm); epi.track(qp);
                 const V4 dyN0 = sub(q1, qm), dyN1 = sub(qp, q0);
                 const V4 dxN0 = dxrow(q0, P1[-1], P1[4]), dxN1 = dxrow(q1, P1[PITCH - 1], P1[PITCH + 4]);
-                epi.template put<1>(0, sub(dyN0, dyP[0]));
-                epi.template put<1>(1, sub(dyN1, dyP[1]));
-                epi.template put<2>(0, sub(dxN0, dxP[0]));
-                epi.template put<2>(1, sub(dxN1, dxP[1]));
-                dyP[0] = dy0; dyP[1] = dy1;
-                dxP[0] = dx0; dxP[1] = dx1;
+                epi.template put<1>(0, sub(dyN0, dyQ[0]));
+                epi.template put<1>(1, sub(dyN1, dyQ[1]));
+                epi.template put<2>(0, sub(dxN0, dxQ[0]));
+                epi.template put<2>(1, sub(dxN1, dxQ[1]));
             }
-            epi.step(cx);
-            // ---- release plane i-K (slot (j - K) mod D) ----
-            if (i >= K) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive_a(sb_empty + 8u * (unsigned)((j - K + D) % D));
+        }
+        epi.step(cx);
+        // ---- release plane i-K; the last warp to let go of it refills the slot with plane i-K+D ----
+        if (i >= K) {
+            __syncwarp();
+            if (lane == 0) {
+                const int pr = i - K;
+                const unsigned slot = (unsigned)pr & (D - 1);
+                __threadfence_block();                       // this warp's reads of the slot are done before the count
+                if (atomicAdd(&rg.released[slot], 1u) == NW - 1) {
+                    atomicExch(&rg.released[slot], 0u);      // next use of the counter comes after the refill landed
+                    if (pr + D < n_pl)
+                        tma_plane_a(sb + slot * (unsigned)(SLOT * 4), map, sb_full + 8u * slot, tx0, ty0, zb0 + pr + D);
+                }
             }
         }
     }
@@ -430,6 +439,7 @@ __device__ __noinline__ void record_max(float mx, bool nan, long long* hstats, u
 
 template <int MODE>
 struct StatsFastEpi {
+    static constexpr bool kLagZ = true;      // components are folded one by one: the march may emit them plane-shifted
     const StatsFastParams& p;
     const Consts& k;
     const Geo& q;
@@ -523,7 +533,7 @@ struct StatsFastEpi {
 // invalid lanes sits in the border shell, whose exact kernel propagates it (store_range).
 
 template <int MODE, int D>
-__global__ void __maxnreg__(NB200_STATS_REGS)
+__global__ void __launch_bounds__(NT, 2)
 stats_fast_kernel(const __grid_constant__ CUtensorMap map, nb200_vol v, Consts k, int zi0, int zi1, int zchunk,
                   StatsFastParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -539,8 +549,9 @@ stats_fast_kernel(const __grid_constant__ CUtensorMap map, nb200_vol v, Consts k
     const int zs = zi0 + (int)b * zchunk;
     const int ze = min(zs + zchunk, zi1);
     if (zs >= ze) return;
+    ring_init(rg, &map, q, zs, ze);
     StatsFastEpi<MODE> epi(p, k, q, zs, ze);
-    march<D, 0, 0>(rg, &map, q, zs, ze, epi);
+    consume<D, 0>(rg, &map, q, zs, ze, epi);
 }
 
 __global__ void wl_reset_kernel(unsigned* wl) {
@@ -551,7 +562,7 @@ __global__ void wl_reset_kernel(unsigned* wl) {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 stats_fixup_kernel(const float* __restrict__ g, nb200_vol v, Consts k, const unsigned* __restrict__ wl,
-                   long long* __restrict__ hstats) {
+                   long long* __restrict__ hstats, int zi0) {
     __shared__ float red[8];
     const unsigned n_all = wl[0];
     const float mt = __uint_as_float((unsigned)hstats[NB200_HS_APPROX_MAX_BITS]);
@@ -569,7 +580,8 @@ stats_fixup_kernel(const float* __restrict__ g, nb200_vol v, Consts k, const uns
     for (unsigned e = blockIdx.x; e < n_all; e += gridDim.x) {
         const unsigned* w = wl + WL_HDR + 8ull * e;
         if (__uint_as_float(w[4]) < thr) continue;
-        const int x0 = (int)w[0], y0 = (int)w[1], z0 = (int)w[2], z1 = (int)w[3];
+        // the record of planes [z0, z1) also holds the mixed Z derivatives of plane z0-1 (lagged emission of the march)
+        const int x0 = (int)w[0], y0 = (int)w[1], z0 = max((int)w[2] - 1, zi0), z1 = (int)w[3];
         float mx = 0.0f;
         const int total = (z1 - z0) * RW * TX;
         for (int t = threadIdx.x; t < total; t += blockDim.x) {
@@ -604,11 +616,11 @@ __device__ __noinline__ float eig_vesselness(float a00, float a01, float a02, fl
     return nb::vesselness3(l1, l2, l3, alpha_sq, beta_sq, gamma_sq);
 }
 
-constexpr int CQ_CAP = 256;           // candidate ring per warp (u8 entries: row << 7 | column)
+constexpr int CQ_CAP = 512;           // candidate ring per warp (u8 entries: row << 7 | column): < 32 left over + <= 256 per step
 constexpr int RQ_CAP = 64;            // survivor stack per warp (< 32 left over + <= 32 pushed)
 struct WarpQueues {
     float rq[7][RQ_CAP];              // six second derivatives + voxel index (uint32 bits)
-    unsigned char cq[CQ_CAP + 64];    // ring indices are taken modulo CQ_CAP; 64 bytes of padding keep rq aligned
+    unsigned char cq[CQ_CAP];         // ring indices are taken modulo CQ_CAP
 };
 
 struct FrangiFastParams {
@@ -620,6 +632,7 @@ struct FrangiFastParams {
 
 template <int MODE, int K>
 struct FrangiFastEpi {
+    static constexpr bool kLagZ = false;     // needs the six components of a voxel together
     const FrangiFastParams& p;
     const Consts& k;
     const Geo& q;
@@ -673,10 +686,11 @@ struct FrangiFastEpi {
         const int e = rq_n - cnt + lane;
         if (lane < cnt) {
             const unsigned at = __float_as_uint(wq.rq[6][e]);
-            const float cur_v = p.acc[at];
             const float vv = eig_vesselness(wq.rq[0][e], wq.rq[1][e], wq.rq[2][e], wq.rq[3][e], wq.rq[4][e], wq.rq[5][e],
                                             p.alpha_sq, p.beta_sq, gamma_sq);
-            if (vv > cur_v) p.acc[at] = vv;             // acc >= 0 here: a zero response changes nothing
+            // acc >= 0 here (only live voxels become candidates) and vv >= 0: non-negative floats order like their bit
+            // patterns, so the running maximum is one fire-and-forget integer RED — no load in front of the solve
+            if (vv > 0.0f) atomicMax(reinterpret_cast<int*>(p.acc) + at, __float_as_int(vv));
         }
         rq_n -= cnt;
         __syncwarp();
@@ -803,44 +817,34 @@ struct FrangiFastEpi {
                 }
             }
         }
-        // ---- push the candidates row by row (warp-aggregated; <= 128 entries per push keep the ring below its
-        //      capacity of 256: at most 31 entries are left over after the full-warp batches) ----
-        const unsigned lt = (1u << lane) - 1u;
+        // ---- push the candidates: one ballot per voxel slot, every lane stays active (the per-lane loop over set bits
+        //      of the first version ran with 14 of 32 threads and cost 12 % of the kernel's instructions) ----
+        if (__ballot_sync(0xffffffffu, cand != 0u) != 0u) {
+            const unsigned lt = (1u << lane) - 1u;
+            int tail = cq_head + cq_n;
 #pragma unroll
-        for (int r = 0; r < RW; ++r) {
-            unsigned c = (cand >> (4 * r)) & 15u;
-            const int cnt = __popc(c);
-            if (__ballot_sync(0xffffffffu, cnt != 0) == 0u) continue;
-            const unsigned b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2);
-            const unsigned b2 = __ballot_sync(0xffffffffu, cnt & 4);
-            int pos = cq_head + cq_n + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-            while (c) {
-                const int b = __ffs(c) - 1;
-                c &= c - 1u;
-                wq.cq[pos & (CQ_CAP - 1)] = (unsigned char)((r << 7) | (4 * lane + b));
-                ++pos;
+            for (int j = 0; j < 4 * RW; ++j) {
+                const bool mine = (cand >> j) & 1u;
+                const unsigned b = __ballot_sync(0xffffffffu, mine);
+                if (mine) wq.cq[(tail + __popc(b & lt)) & (CQ_CAP - 1)] = (unsigned char)(((j >> 2) << 7) | (4 * lane + (j & 3)));
+                tail += __popc(b);
             }
-            cq_n += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-            d_cand += (unsigned long long)cnt;
-            while (cq_n >= 32) batch(cx, 32);
+            const int added = tail - cq_head - cq_n;
+            cq_n += added;
+            d_cand += (unsigned long long)(lane == 0 ? added : 0);
         }
-        // ---- drain: full warps first; then whatever still belongs to a plane that is about to be released ----
-        if (K == 0) {
-            if (cq_n > 0) batch(cx, cq_n);
-        } else {
-            while (cq_old > 0) batch(cx, cq_n < 32 ? cq_n : 32);
-        }
+        // ---- drain (ONE call site: the exact evaluation is the bulk of the kernel's code): full warps first, then
+        //      whatever still belongs to a plane that is about to leave the ring ----
+        while (cq_n >= 32 || (K == 0 ? cq_n > 0 : cq_old > 0)) batch(cx, cq_n < 32 ? cq_n : 32);
 #pragma unroll
         for (int j = 0; j < 5; ++j) prev_sl[j] = cx.sl[j];
         last = cx;
     }
     StepCtx last;
     __device__ void finish() {
-        while (cq_n > 0) {                              // K > 0: candidates of the last plane
-            cq_old = 0;
-            batch(last, cq_n < 32 ? cq_n : 32);
-        }
-        while (rq_n > 0) solve(rq_n < 32 ? rq_n : 32);
+        cq_old = 0;
+        while (cq_n > 0) batch(last, cq_n < 32 ? cq_n : 32);     // K > 0: candidates of the last plane
+        if (rq_n > 0) solve(rq_n);
         if (p.diag != nullptr) {
             for (int o = 16; o > 0; o >>= 1) {
                 d_cand += __shfl_xor_sync(0xffffffffu, d_cand, o);
@@ -863,7 +867,7 @@ struct FrangiSmem {
 };
 
 template <int MODE, int D, int K, int L, int MINB>
-__global__ void __maxnreg__(MINB == 3 ? 96 : 128)
+__global__ void __launch_bounds__(NT, MINB)
 frangi_fast_kernel(const __grid_constant__ CUtensorMap map, nb200_vol v, Consts k, int zi0, int zi1, int zchunk,
                    FrangiFastParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -880,8 +884,9 @@ frangi_fast_kernel(const __grid_constant__ CUtensorMap map, nb200_vol v, Consts 
     const int zs = zi0 + (int)b * zchunk;
     const int ze = min(zs + zchunk, zi1);
     if (zs >= ze) return;
+    ring_init(sm.ring, &map, q, zs, ze);
     FrangiFastEpi<MODE, K> epi(p, k, q, sm.wq);
-    march<D, K, L>(sm.ring, &map, q, zs, ze, epi);
+    consume<D, K>(sm.ring, &map, q, zs, ze, epi);
 }
 
 Consts consts_from(const float* spacing) {
@@ -898,6 +903,55 @@ Consts consts_from(const float* spacing) {
     }
     k.iso = (k.d2[0] == k.d2[1] && k.d2[1] == k.d2[2]) ? 1 : 0;
     return k;
+}
+
+// Interior of the compute window in tiles of TX x TYO columns; Z chunks sized for several waves of 2 CTAs/SM, no
+// shorter than 32 planes (same policy as nb::plan_march, other tile height)
+nb::MarchPlan plan_fast(const nb200_vol& v) {
+    nb::MarchPlan m;
+    const int g0 = v.zc0 + v.zg_off, g1 = v.zc1 + v.zg_off;
+    m.zi0 = max(g0, 2);
+    m.zi1 = min(g1, v.nz_glob - 2);
+    m.zchunk = 0;
+    m.n_ctas = 0;
+    if (m.zi1 <= m.zi0 || v.ny < 5 || v.nx < 12) return m;
+    const long long tiles = (long long)((v.nx + TX - 1) / TX) * ((v.ny - 4 + TYO - 1) / TYO);
+    const int nz = m.zi1 - m.zi0;
+    const long long want = 16LL * nb::sm_count();
+    long long chunks = (want + tiles - 1) / tiles;
+    if (chunks < 1) chunks = 1;
+    int zchunk = (int)((nz + chunks - 1) / chunks);
+    if (zchunk < 32) zchunk = nz < 32 ? nz : 32;
+    chunks = (nz + zchunk - 1) / zchunk;
+    m.zchunk = zchunk;
+    m.n_ctas = tiles * chunks;
+    return m;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// TMA descriptor of the (nz_buf, ny, nx) float32 volume with a box of one staged plane tile (PITCH x GR floats)
+bool make_map_fast(const float* g, const nb200_vol& v, CUtensorMap* map) {
+    memset(map, 0, sizeof(*map));
+    static EncodeTiledFn enc = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            enc = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)v.nx, (cuuint64_t)v.ny, (cuuint64_t)v.nz_buf};
+    const cuuint64_t strides[2] = {(cuuint64_t)v.nx * 4ull, (cuuint64_t)v.nx * (cuuint64_t)v.ny * 4ull};
+    const cuuint32_t box[3] = {(cuuint32_t)PITCH, (cuuint32_t)GR, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(g), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int fast_supported(const float* g, const nb200_vol& v, int div_mode, const char* who) {
@@ -921,7 +975,7 @@ int set_smem(Kern kernel, size_t bytes, bool& done) {
     return NB200_OK;
 }
 
-constexpr int D_STATS = 7;
+constexpr int D_STATS = 8;
 
 template <int MODE>
 int launch_stats(const CUtensorMap& map, const float* g, const nb200_vol& v, const Consts& k, const nb::MarchPlan& m,
@@ -933,7 +987,7 @@ int launch_stats(const CUtensorMap& map, const float* g, const nb200_vol& v, con
     kernel<<<(unsigned)m.n_ctas, NT, sizeof(Ring<D_STATS>), st>>>(map, v, k, m.zi0, m.zi1, m.zchunk, p);
     rc = nb::check_launch("hessian_stats_fast");
     if (rc) return rc;
-    stats_fixup_kernel<MODE><<<2 * nb::sm_count(), 256, 0, st>>>(g, v, k, p.wl, p.hstats);
+    stats_fixup_kernel<MODE><<<2 * nb::sm_count(), 256, 0, st>>>(g, v, k, p.wl, p.hstats, m.zi0);
     return nb::check_launch("hessian_stats_fast(fixup)");
 }
 
@@ -953,9 +1007,7 @@ int launch_frangi(const CUtensorMap& map, const nb200_vol& v, const Consts& k, c
                   const FrangiFastParams& p, cudaStream_t st) {
     static const int cfg = getenv("NB200_FAST_CFG") ? atoi(getenv("NB200_FAST_CFG")) : 0;
     switch (cfg) {
-        case 1: return launch_frangi_cfg<MODE, 7, 0, 0, 2>(map, v, k, m, p, st);
-        case 2: return launch_frangi_cfg<MODE, 9, 1, 1, 2>(map, v, k, m, p, st);
-        case 3: return launch_frangi_cfg<MODE, 6, 0, 0, 3>(map, v, k, m, p, st);
+        case 1: return launch_frangi_cfg<MODE, 8, 0, 0, 2>(map, v, k, m, p, st);
         default: return launch_frangi_cfg<MODE, 8, 1, 0, 2>(map, v, k, m, p, st);
     }
 }
@@ -991,10 +1043,10 @@ int nb200_hessian_stats_fast(const float* gauss, const nb200_vol* vol, const flo
     hf::wl_reset_kernel<<<1, 32, 0, st>>>(p.wl);
     rc = nb::check_launch("hessian_stats_fast(reset)");
     if (rc) return rc;
-    const nb::MarchPlan m = nb::plan_march(v);
+    const nb::MarchPlan m = hf::plan_fast(v);
     if (m.n_ctas > 0) {
         CUtensorMap map;
-        NB_REQUIRE(nb::make_plane_map(gauss, v, &map), NB200_ERR_UNSUPPORTED,
+        NB_REQUIRE(hf::make_map_fast(gauss, v, &map), NB200_ERR_UNSUPPORTED,
                    "nb200_hessian_stats_fast: no TMA descriptor for this volume");
         const hf::Consts k = hf::consts_from(spacing);
         rc = div_mode == hm::DIV_POW2 ? hf::launch_stats<2>(map, gauss, v, k, m, p, st)
@@ -1017,10 +1069,10 @@ int nb200_frangi_fast(const float* gauss, float* acc, const nb200_vol* vol, cons
                "nb200_frangi_fast: acc must be 16-byte aligned");
     if (v.zc0 == v.zc1) return NB200_OK;
     cudaStream_t st = nb::as_stream(stream);
-    const nb::MarchPlan m = nb::plan_march(v);
+    const nb::MarchPlan m = hf::plan_fast(v);
     if (m.n_ctas > 0) {
         CUtensorMap map;
-        NB_REQUIRE(nb::make_plane_map(gauss, v, &map), NB200_ERR_UNSUPPORTED,
+        NB_REQUIRE(hf::make_map_fast(gauss, v, &map), NB200_ERR_UNSUPPORTED,
                    "nb200_frangi_fast: no TMA descriptor for this volume");
         const hf::Consts k = hf::consts_from(spacing);
         hf::FrangiFastParams p;

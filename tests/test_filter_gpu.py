@@ -299,7 +299,7 @@ def test_2d_cuda_graph_replay_equals_eager_launches():
     want = [eager.filter_frame(f).clone() for f in frames]
     eng = FrangiEngine2D(shape, FilterParams(dim_res=dim_res, no_z=True), device="cuda")
     got = [eng.filter_frame(f).clone() for f in frames]
-    assert eng.use_graph and True in eng._graphs, "graph capture did not happen"
+    assert eng.use_graph and (True, True) in eng._graphs, "graph capture did not happen"
     for t in range(5):
         assert torch.equal(got[t], want[t]), t
     assert any(bool((w > 0).any()) for w in want)
