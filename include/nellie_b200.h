@@ -93,6 +93,10 @@ typedef struct nb200_vol {
                                      volume (nb200_finalize_max_abs then sets sp[UNSAFE]: the exact passes take over) */
 #define NB200_HS_WORDS 8
 
+/* int64[NB200_STATE_WORDS]: histogram state followed by the Hessian stats record, contiguous, so that a Z-sharded
+ * caller moves both with ONE all-gather per reduction point (nb200_fold_records) */
+#define NB200_STATE_WORDS (NB200_HIST_WORDS + NB200_HS_WORDS)
+
 int nb200_abi_version(void);
 const char* nb200_last_error(void);
 /* number of SMs of the current device (grid sizing is a multiple of it) */
@@ -133,6 +137,11 @@ int nb200_hist_minmax(const float* vals, long long n, int transform, const doubl
                       long long* state, void* stream);
 int nb200_hist_bins(const float* vals, long long n, int transform, const double* divisor,
                     long long* state, void* stream);
+/* Multi-GPU reduction of the threshold state ("pack into <= 2 calls"): `gathered` holds the
+ * NB200_STATE_WORDS-word records of all `world` ranks (rank-major, e.g. from ncclAllGather); folds them into `state`.
+ * stage 0: HIST_MIN -> min, HIST_MAX -> max, Hessian stats -> max (every stats word reduces with MAX);
+ * stage 1: HIST_COUNT and the 256 bins -> sum, Hessian stats -> max.  Other words of `state` are left alone. */
+int nb200_fold_records(const long long* gathered, int world, int stage, long long* state, void* stream);
 /* gamma = min(triangle, otsu) (filtering.py:365-380) -> sp[GAMMA], sp[GAMMA_SQ] */
 int nb200_finalize_gamma(const long long* state, double* sp, void* stream);
 /* Frobenius threshold (filtering.py:407-444): consumes the histogram of frob samples and the

@@ -19,6 +19,8 @@ HS_MAX_ABS_BITS, HS_MAX_FROBSQ_BITS, HS_MIN_NZ_COMPL, HS_MAX_G_BITS, HS_APPROX_M
 DIV_IEEE, DIV_FAST, DIV_POW2 = 0, 1, 2
 TF_NONE, TF_DIV, TF_LOG10 = 0, 1, 2
 SELECT_WORDS = 2048 + 8
+STATE_WORDS = HIST_WORDS + HS_WORDS
+FOLD_MINMAX, FOLD_BINS = 0, 1
 
 ERR_OOM = -3
 
@@ -75,6 +77,7 @@ _SIGS = {
                                  C.c_int),
     "nb200_finalize_frob_fast": ([_p, _p, C.c_double, C.c_double, C.c_double, C.c_int, _p, _p], C.c_int),
     "nb200_finalize_frob_resolve": ([_p, _p, _p], C.c_int),
+    "nb200_fold_records": ([_p, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_frangi_fast": ([_p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, _p, _p, _p], C.c_int),
     "nb200_hessian_components": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, _p], C.c_int),
     "nb200_divisor_mode": ([C.c_float, C.POINTER(C.c_int), _p], C.c_int),
@@ -98,7 +101,8 @@ _lib = None
 
 
 def lib_path() -> str:
-    return _build.LIB
+    # NB200_LIB: an alternative build of the same library (kernel experiments: scripts/build_variant.sh)
+    return os.environ.get("NB200_LIB") or _build.LIB
 
 
 def load():

@@ -40,6 +40,10 @@
 #include "hessian_march.cuh"
 #include "march_host.cuh"
 
+#ifndef NB200_STATS_CTAS
+#define NB200_STATS_CTAS 2
+#define NB200_STATS_D 8
+#endif
 #ifndef NB200_MARCH_UNROLL
 #define NB200_MARCH_UNROLL 1
 #endif
@@ -222,7 +226,6 @@ struct StepCtx {
 // polling an empty-mbarrier issued 14 % of the kernel's instructions, and the eighth warp slot of the CTA was wasted.)
 template <int D>
 __device__ __forceinline__ void ring_init(Ring<D>& rg, const CUtensorMap* map, const Geo& q, int zs, int ze) {
-    static_assert((D & (D - 1)) == 0, "ring depth must be a power of two");
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
@@ -251,7 +254,7 @@ __device__ __forceinline__ void consume(Ring<D>& rg, const CUtensorMap* map, con
     const float* ring = &rg.g[0][0];
     const unsigned sb = hm::smem_u32(&rg);
     const unsigned sb_full = sb + (unsigned)(sizeof(float) * D * SLOT);
-    auto wait_full = [&](int p) { mbar_wait_a<NB200_SLEEP_CONSUMER>(sb_full + 8u * ((unsigned)p & (D - 1)), (unsigned)(p / D) & 1u); };
+    auto wait_full = [&](int p) { mbar_wait_a<NB200_SLEEP_CONSUMER>(sb_full + 8u * ((unsigned)p % D), ((unsigned)p / D) & 1u); };
     V4 a0[RW], a1[RW], dyP[RW], dxP[RW], dyQ[RW], dxQ[RW];
 #pragma unroll
     for (int r = 0; r < RW; ++r) { dyQ[r] = V4(); dxQ[r] = V4(); }
@@ -284,7 +287,7 @@ __device__ __forceinline__ void consume(Ring<D>& rg, const CUtensorMap* map, con
         cx.off0 = off0;
         cx.o = zs + i;
 #pragma unroll
-        for (int t = 0; t < 5; ++t) cx.sl[t] = (i + t) & (D - 1);
+        for (int t = 0; t < 5; ++t) cx.sl[t] = (int)((unsigned)(i + t) % D);
         wait_full(i + 4);
         const float* P0 = base + cx.sl[2] * SLOT;     // plane o
         const float* P1 = base + cx.sl[3] * SLOT;     // plane o+1
@@ -367,7 +370,7 @@ __device__ __forceinline__ void consume(Ring<D>& rg, const CUtensorMap* map, con
             __syncwarp();
             if (lane == 0) {
                 const int pr = i - K;
-                const unsigned slot = (unsigned)pr & (D - 1);
+                const unsigned slot = (unsigned)pr % D;
                 __threadfence_block();                       // this warp's reads of the slot are done before the count
                 if (atomicAdd(&rg.released[slot], 1u) == NW - 1) {
                     atomicExch(&rg.released[slot], 0u);      // next use of the counter comes after the refill landed
@@ -533,7 +536,7 @@ struct StatsFastEpi {
 // invalid lanes sits in the border shell, whose exact kernel propagates it (store_range).
 
 template <int MODE, int D>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, NB200_STATS_CTAS)
 stats_fast_kernel(const __grid_constant__ CUtensorMap map, nb200_vol v, Consts k, int zi0, int zi1, int zchunk,
                   StatsFastParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -975,7 +978,7 @@ int set_smem(Kern kernel, size_t bytes, bool& done) {
     return NB200_OK;
 }
 
-constexpr int D_STATS = 8;
+constexpr int D_STATS = NB200_STATS_D;
 
 template <int MODE>
 int launch_stats(const CUtensorMap& map, const float* g, const nb200_vol& v, const Consts& k, const nb::MarchPlan& m,

@@ -164,89 +164,136 @@ struct TwoThresholds {
     int status;  // 0 ok, 1 degenerate (reference raises / yields NaN)
 };
 
-__device__ TwoThresholds otsu_triangle(const long long* state, double* work /* >= 4*NB doubles */) {
-    TwoThresholds r; r.tri = 0.f; r.otsu = 0.f; r.status = 0;
+// Block-cooperative (256 threads, all must call).  The cumulative sums run in ONE thread in index order, like
+// np.cumsum; everything without a loop-carried dependency (normalised counts, products, the 2 x 255 float64 divisions of
+// the class means, the between-class variance, the triangle distances) is spread over the block.  The single-thread
+// form took ~100 us per call (12 calls per frame, and the part of a Z-sharded step that does not shrink with GPUs).
+constexpr int FIN_THREADS = 256;
+struct FinalizeScratch {
+    float edges[NB + 1];
+    float centers[NB];
+    double p[NB], pc[NB], w_lo[NB], s_lo[NB], w_hi[NB], s_hi[NB], val[NB];
+    long long total;
+    int arg;
+    TwoThresholds out;
+};
+
+__device__ TwoThresholds otsu_triangle(const long long* state, FinalizeScratch& w) {
+    const int t = threadIdx.x;
     float first, last;
     outer_edges(state, first, last);
-    __shared__ float edges[NB + 1];
-    __shared__ float centers[NB];
-    build_edges(first, last, edges, 0, 1);
-    for (int i = 0; i < NB; ++i) centers[i] = (edges[i] + edges[i + 1]) / 2.0f;
-    double* p = work;            // normalised counts
-    double* w_hi = work + NB;    // reverse cumulative weight
-    double* s_hi = work + 2 * NB;  // reverse cumulative p*c
-    long long total = 0;
-    for (int i = 0; i < NB; ++i) total += state[NB200_HIST_BINS + i];
-    const double dt = (double)total;
-    for (int i = 0; i < NB; ++i) p[i] = (double)state[NB200_HIST_BINS + i] / dt;
+    build_edges(first, last, w.edges, t, FIN_THREADS);
+    if (t == 0) {
+        long long total = 0;
+        for (int i = 0; i < NB; ++i) total += state[NB200_HIST_BINS + i];
+        w.total = total;
+        w.out.tri = 0.f; w.out.otsu = 0.f; w.out.status = 0;
+    }
+    __syncthreads();
+    if (t < NB) {
+        w.centers[t] = (w.edges[t] + w.edges[t + 1]) / 2.0f;
+        w.p[t] = (double)state[NB200_HIST_BINS + t] / (double)w.total;
+        w.pc[t] = w.p[t] * (double)w.centers[t];
+    }
+    __syncthreads();
     // ---- Otsu (gpu_functions.py:36-50)
-    {
+    if (t == 0) {                    // reverse cumulative weight / weighted sum
         double aw = 0.0, as = 0.0;
         for (int i = NB - 1; i >= 0; --i) {
-            aw = aw + p[i];
-            as = as + p[i] * (double)centers[i];
-            w_hi[i] = aw;
-            s_hi[i] = as;
+            aw = aw + w.p[i];
+            as = as + w.pc[i];
+            w.w_hi[i] = aw;
+            w.s_hi[i] = as;
         }
-        double w_lo = 0.0, s_lo = 0.0, best = 0.0;
+    } else if (t == 32) {            // forward ones, on another warp
+        double aw = 0.0, as = 0.0;
+        for (int i = 0; i < NB; ++i) {
+            aw = aw + w.p[i];
+            as = as + w.pc[i];
+            w.w_lo[i] = aw;
+            w.s_lo[i] = as;
+        }
+    }
+    __syncthreads();
+    if (t < NB - 1) {
+        const double m_lo = w.s_lo[t] / w.w_lo[t];
+        const double m_hi = w.s_hi[t + 1] / w.w_hi[t + 1];
+        const double d = m_lo - m_hi;
+        w.val[t] = (w.w_lo[t] * w.w_hi[t + 1]) * (d * d);
+    }
+    __syncthreads();
+    if (t == 0) {
+        double best = 0.0;
         int arg = 0;
         bool have = false, nan_hit = false;
         for (int i = 0; i < NB - 1; ++i) {
-            w_lo = w_lo + p[i];
-            s_lo = s_lo + p[i] * (double)centers[i];
-            const double m_lo = s_lo / w_lo;
-            const double m_hi = s_hi[i + 1] / w_hi[i + 1];
-            const double d = m_lo - m_hi;
-            const double var = (w_lo * w_hi[i + 1]) * (d * d);
+            const double var = w.val[i];
             if (var != var) {  // np.argmax returns the first NaN
                 if (!nan_hit) { arg = i; nan_hit = true; }
             } else if (!nan_hit && (!have || var > best)) {
                 best = var; arg = i; have = true;
             }
         }
-        if (nan_hit) r.status = 1;
-        r.otsu = centers[arg];
+        if (nan_hit) w.out.status = 1;
+        w.out.otsu = w.centers[arg];
     }
+    __syncthreads();
     // ---- triangle (gpu_functions.py:65-94)
-    {
+    __shared__ int tri_lo, tri_peak, tri_width, tri_flip;
+    __shared__ double tri_hn, tri_wn;
+    if (t == 0) {
         int peak = 0;
-        double hpk = p[0];
-        for (int i = 1; i < NB; ++i) if (p[i] > hpk) { hpk = p[i]; peak = i; }
+        double hpk = w.p[0];
+        for (int i = 1; i < NB; ++i) if (w.p[i] > hpk) { hpk = w.p[i]; peak = i; }
         int lo = 0, hi = NB - 1;
-        while (lo < NB - 1 && !(p[lo] != 0.0)) ++lo;
-        while (hi > 0 && !(p[hi] != 0.0)) --hi;
+        while (lo < NB - 1 && !(w.p[lo] != 0.0)) ++lo;
+        while (hi > 0 && !(w.p[hi] != 0.0)) --hi;
         const bool flip = (peak - lo) < (hi - peak);
         if (flip) { lo = NB - hi - 1; peak = NB - peak - 1; }
         const int width = peak - lo;
+        tri_lo = lo; tri_peak = peak; tri_width = width; tri_flip = flip ? 1 : 0;
         if (width <= 0) {
-            r.status = 1;  // np.argmax of an empty array raises ValueError in the reference
-            r.tri = centers[flip ? NB - lo - 1 : lo];
+            w.out.status = 1;  // np.argmax of an empty array raises ValueError in the reference
+            w.out.tri = w.centers[flip ? NB - lo - 1 : lo];
         } else {
             const double nrm = sqrt(hpk * hpk + (double)((long long)width * width));
-            const double hn = hpk / nrm, wn = (double)width / nrm;
-            double best = 0.0; int arg = 0;
-            for (int x = 0; x < width; ++x) {
-                const int src = x + lo;
-                const double y = flip ? p[NB - 1 - src] : p[src];
-                const double len = hn * (double)x - wn * y;
-                if (x == 0 || len > best) { best = len; arg = x; }
-            }
-            int lvl = arg + lo;
-            if (flip) lvl = NB - lvl - 1;
-            r.tri = centers[lvl];
+            tri_hn = hpk / nrm;
+            tri_wn = (double)width / nrm;
         }
     }
-    return r;
+    __syncthreads();
+    if (tri_width > 0) {
+        if (t < tri_width) {
+            const int src = t + tri_lo;
+            const double y = tri_flip ? w.p[NB - 1 - src] : w.p[src];
+            w.val[t] = tri_hn * (double)t - tri_wn * y;
+        }
+        __syncthreads();
+        if (t == 0) {
+            double best = 0.0; int arg = 0;
+            for (int x = 0; x < tri_width; ++x) {
+                const double len = w.val[x];
+                if (x == 0 || len > best) { best = len; arg = x; }
+            }
+            int lvl = arg + tri_lo;
+            if (tri_flip) lvl = NB - lvl - 1;
+            w.out.tri = w.centers[lvl];
+        }
+    }
+    __syncthreads();
+    return w.out;
 }
 
-__global__ void finalize_gamma_kernel(const long long* state, double* sp) {
-    __shared__ double work[4 * NB];
-    if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(FIN_THREADS) finalize_gamma_kernel(const long long* state, double* sp) {
+    __shared__ FinalizeScratch work;
     const double eps = 1.1920928955078125e-07;  // np.finfo(np.float32).eps
     double gamma = eps;
     double status = 0.0;
-    if (state[NB200_HIST_COUNT] > 0) {
-        const TwoThresholds t = otsu_triangle(state, work);
+    const bool have = state[NB200_HIST_COUNT] > 0;      // block-uniform
+    TwoThresholds t;
+    if (have) t = otsu_triangle(state, work);
+    if (threadIdx.x != 0) return;
+    if (have) {
         sp[NB200_SP_TRI] = (double)t.tri;
         sp[NB200_SP_OTSU] = (double)t.otsu;
         gamma = (double)fminf(t.tri, t.otsu);
@@ -278,9 +325,13 @@ __global__ void finalize_max_abs_kernel(const long long* hstats, double* sp) {
 
 // fast != 0: no exact max frob_sq unless the exact redo pass ran (sp[UNSAFE]); emptiness of the mask from the bounds
 // 1 <= max frob <= 3, classification thresholds of nb200_frangi_fast from the proven error bound (hessian_fast.cu)
-__global__ void finalize_frob_kernel(const long long* state, const long long* hstats, double fixed_thresh,
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_frob_kernel(const long long* state, const long long* hstats, double fixed_thresh,
                                      double division, double* sp, int fast, double max_scale, int mask_enabled) {
-    __shared__ double work[4 * NB];
+    __shared__ FinalizeScratch work;
+    const bool use_hist = mask_enabled && !(fixed_thresh == fixed_thresh) && state[NB200_HIST_COUNT] > 0;   // block-uniform
+    TwoThresholds t;
+    if (use_hist) t = otsu_triangle(state, work);
     if (threadIdx.x != 0) return;
     double thr = 0.0;
     double status = sp[NB200_SP_STATUS];
@@ -288,8 +339,7 @@ __global__ void finalize_frob_kernel(const long long* state, const long long* hs
         thr = 0.0;
     } else if (fixed_thresh == fixed_thresh) {
         thr = fixed_thresh;
-    } else if (state[NB200_HIST_COUNT] > 0) {
-        const TwoThresholds t = otsu_triangle(state, work);
+    } else if (use_hist) {
         thr = (double)fminf(t.tri, t.otsu);
         if (t.status) status = 1.0;
     }
@@ -361,6 +411,27 @@ __global__ void finalize_frob_kernel(const long long* state, const long long* hs
     sp[NB200_SP_STATUS] = status;
 }
 
+// Z-sharded frames: every rank all-gathers its [histogram state | Hessian stats] record; this kernel folds the gathered
+// records into the local one with the right operator per word (identical result on every rank).
+//   stage 0 (after hist_minmax / hessian stats): word MIN -> min, word MAX -> max, Hessian stats -> max
+//   stage 1 (after hist_bins):                    count + 256 bins -> sum,          Hessian stats -> max
+__global__ void fold_records_kernel(const long long* __restrict__ gathered, int world, int stage, long long* __restrict__ state) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NB200_STATE_WORDS) return;
+    const bool is_hs = i >= NB200_HIST_WORDS;
+    int op = -1;                                   // 0 min, 1 max, 2 sum
+    if (is_hs) op = 1;
+    else if (stage == 0) op = i == NB200_HIST_MIN ? 0 : (i == NB200_HIST_MAX ? 1 : -1);
+    else op = i >= NB200_HIST_COUNT ? 2 : -1;
+    if (op < 0) return;
+    long long acc = gathered[i];
+    for (int r = 1; r < world; ++r) {
+        const long long v = gathered[(long long)r * NB200_STATE_WORDS + i];
+        acc = op == 0 ? (v < acc ? v : acc) : (op == 1 ? (v > acc ? v : acc) : acc + v);
+    }
+    state[i] = acc;
+}
+
 __global__ void finalize_frob_resolve_kernel(const long long* hstats, double* sp) {
     if (threadIdx.x != 0 || sp[NB200_SP_AMBIG] == 0.0 || sp[NB200_SP_UNSAFE] != 0.0) return;
     const float max_abs = (float)sp[NB200_SP_MAX_ABS];
@@ -369,12 +440,14 @@ __global__ void finalize_frob_resolve_kernel(const long long* hstats, double* sp
     sp[NB200_SP_AMBIG] = 0.0;
 }
 
-__global__ void finalize_label_kernel(const long long* state, int log_domain, double* out) {
-    __shared__ double work[4 * NB];
+__global__ void __launch_bounds__(FIN_THREADS) finalize_label_kernel(const long long* state, int log_domain, double* out) {
+    __shared__ FinalizeScratch work;
+    const bool have = state[NB200_HIST_COUNT] > 0;      // block-uniform
+    TwoThresholds t;
+    if (have) t = otsu_triangle(state, work);
     if (threadIdx.x != 0) return;
     out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; out[3] = 1.0; out[4] = 0.0;
-    if (state[NB200_HIST_COUNT] <= 0) return;
-    const TwoThresholds t = otsu_triangle(state, work);
+    if (!have) return;
     out[3] = 0.0;
     out[4] = (double)t.status;
     if (log_domain) {
@@ -551,7 +624,7 @@ int nb200_hist_bins(const float* vals, long long n, int transform, const double*
 
 int nb200_finalize_gamma(const long long* state, double* sp, void* stream) {
     NB_REQUIRE(state && sp, NB200_ERR_ARG, "nb200_finalize_gamma: null argument");
-    finalize_gamma_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(state, sp);
+    finalize_gamma_kernel<<<1, FIN_THREADS, 0, nb::as_stream(stream)>>>(state, sp);
     return nb::check_launch("finalize_gamma");
 }
 
@@ -564,16 +637,22 @@ int nb200_finalize_max_abs(const long long* hstats, double* sp, void* stream) {
 int nb200_finalize_frob(const long long* state, const long long* hstats, double fixed_thresh, double division,
                         double* sp, void* stream) {
     NB_REQUIRE(state && hstats && sp, NB200_ERR_ARG, "nb200_finalize_frob: null argument");
-    finalize_frob_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(state, hstats, fixed_thresh, division, sp, 0, 0.0, 1);
+    finalize_frob_kernel<<<1, FIN_THREADS, 0, nb::as_stream(stream)>>>(state, hstats, fixed_thresh, division, sp, 0, 0.0, 1);
     return nb::check_launch("finalize_frob");
 }
 
 int nb200_finalize_frob_fast(const long long* state, const long long* hstats, double fixed_thresh, double division,
                              double max_scale, int mask_enabled, double* sp, void* stream) {
     NB_REQUIRE(state && hstats && sp && max_scale >= 0.0, NB200_ERR_ARG, "nb200_finalize_frob_fast: bad argument");
-    finalize_frob_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(state, hstats, fixed_thresh, division, sp,
+    finalize_frob_kernel<<<1, FIN_THREADS, 0, nb::as_stream(stream)>>>(state, hstats, fixed_thresh, division, sp,
                                                               max_scale > 0.0 ? 1 : 0, max_scale, mask_enabled);
     return nb::check_launch("finalize_frob_fast");
+}
+
+int nb200_fold_records(const long long* gathered, int world, int stage, long long* state, void* stream) {
+    NB_REQUIRE(gathered && state && world >= 1 && (stage == 0 || stage == 1), NB200_ERR_ARG, "nb200_fold_records: bad argument");
+    fold_records_kernel<<<(NB200_STATE_WORDS + 255) / 256, 256, 0, nb::as_stream(stream)>>>(gathered, world, stage, state);
+    return nb::check_launch("fold_records");
 }
 
 int nb200_finalize_frob_resolve(const long long* hstats, double* sp, void* stream) {
@@ -584,7 +663,7 @@ int nb200_finalize_frob_resolve(const long long* hstats, double* sp, void* strea
 
 int nb200_finalize_label_threshold(const long long* state, int log_domain, double* out, void* stream) {
     NB_REQUIRE(state && out, NB200_ERR_ARG, "nb200_finalize_label_threshold: null argument");
-    finalize_label_kernel<<<1, 32, 0, nb::as_stream(stream)>>>(state, log_domain, out);
+    finalize_label_kernel<<<1, FIN_THREADS, 0, nb::as_stream(stream)>>>(state, log_domain, out);
     return nb::check_launch("finalize_label_threshold");
 }
 

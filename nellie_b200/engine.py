@@ -181,8 +181,11 @@ class FrangiEngine3D:
         self.acc = torch.empty((self.nz_buf, ny, nx), **f32)
         self.out = torch.empty((self.nz_own, ny, nx), **f32)
         self.samples = torch.empty(max(1, self.n_samples), **f32)
-        self.hist = torch.zeros(_cabi.HIST_WORDS, dtype=torch.int64, device=dev)
-        self.hstats = torch.zeros(_cabi.HS_WORDS, dtype=torch.int64, device=dev)
+        self.frob_samples = torch.empty(max(1, self.n_samples), **f32)   # fast path: frob samples next to the gauss samples
+        # histogram state and Hessian stats live in ONE record: a Z-sharded run moves both with one all-gather
+        self.state = torch.zeros(_cabi.STATE_WORDS, dtype=torch.int64, device=dev)
+        self.hist = self.state[:_cabi.HIST_WORDS]
+        self.hstats = self.state[_cabi.HIST_WORDS:]
         self.sp = torch.zeros((len(self.sigmas), _cabi.SP_WORDS), dtype=torch.float64, device=dev)
         self.select = torch.zeros(_cabi.SELECT_WORDS, dtype=torch.int64, device=dev)
         self.pct = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -209,6 +212,7 @@ class FrangiEngine3D:
         self.reduce_hist_minmax = lambda state: None
         self.reduce_hist_bins = lambda state: None
         self.reduce_hstats = lambda hs: None
+        self.fold_state = lambda state, stage: None      # fast path: one packed reduction per reduction point
         self.gather_samples = lambda s, n: (s, n)
 
     def _pick_div_mode(self):
@@ -325,17 +329,17 @@ class FrangiEngine3D:
         sp_i = self.sp[i]
         sz, sy, sx = self.strides
         own = self.vol()
+        fixed = float("nan") if self.p.frob_thresh is None else float(self.p.frob_thresh)
+        division = float(self.p.frob_thresh_division or 0.0)
+        mask_on = 1 if self.p.mask else 0
+        if self.fast_path:
+            self._analyse_sigma_fast(i, g, own, sp_i, fixed, division, mask_on, st)
+            return
         # F2/F3: gamma from the positive lattice sample of the blurred volume
         self._call("nb200_lattice_sample", _ptr(g), C.byref(own), sz, sy, sx, _ptr(self.samples), st)
         self._histogram(self.samples, self.n_samples, _cabi.TF_NONE, None)
         self._call("nb200_finalize_gamma", _ptr(self.hist), _ptr(sp_i), st)
-        fixed = float("nan") if self.p.frob_thresh is None else float(self.p.frob_thresh)
-        division = float(self.p.frob_thresh_division or 0.0)
-        mask_on = 1 if self.p.mask else 0
         self._call("nb200_hstats_reset", _ptr(self.hstats), st)
-        if self.fast_path:
-            self._analyse_sigma_fast(i, g, own, sp_i, fixed, division, mask_on, st)
-            return
         # F4: Hessian statistics (max|H|, max frob^2, frob samples) + K2's per-voxel record for the sparse K3
         code = self.code if self.sparse_k3 else None
         self._call("nb200_hessian_stats_code", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
@@ -376,26 +380,46 @@ class FrangiEngine3D:
             self._call("nb200_hist_reset", _ptr(self.hist), st)
 
     def _analyse_sigma_fast(self, i, g, own, sp_i, fixed, division, mask_on, st):
-        """F4-F9 through hessian_fast.cu.  Every exact fallback is enqueued behind a device flag: the kernels return at
-        once unless the statistics pass raised sp[UNSAFE] (value range / exactness argument) or sp[AMBIG]."""
+        """F2-F9 through hessian_fast.cu.  Every exact fallback is enqueued behind a device flag: the kernels return at
+        once unless the statistics pass raised sp[UNSAFE] (value range / exactness argument) or sp[AMBIG].
+
+        Reduction points of a Z-sharded frame (``fold_state``: one all-gather of the 267-word record + one fold kernel
+        each; identity on one GPU): [gauss min/max + Hessian stats] -> [gauss bins + stats of the exact redo] ->
+        [frob min/max] -> [frob bins] -> [exact max frob^2 when the mask's emptiness was undecided]."""
         sz, sy, sx = self.strides
         a_sq, b_sq = float(self.p.alpha_sq), float(self.p.beta_sq)
+        n = self.n_samples
+        auto_thr = bool(mask_on) and self.p.frob_thresh is None and division != 0.0
+        # F2/F3 (first half) + F4 statistics
+        self._call("nb200_lattice_sample", _ptr(g), C.byref(own), sz, sy, sx, _ptr(self.samples), st)
+        self._call("nb200_hist_reset", _ptr(self.hist), st)
+        self._call("nb200_hist_minmax", _ptr(self.samples), n, _cabi.TF_NONE, None, _ptr(self.hist), st)
+        self._call("nb200_hstats_reset", _ptr(self.hstats), st)
         self._call("nb200_hessian_stats_fast", _ptr(g), C.byref(own), self._fd_c, self.div_mode, sz, sy, sx,
-                   _ptr(self.samples), _ptr(self.hstats), _ptr(self.fast_ws), st)
-        self.reduce_hstats(self.hstats)
+                   _ptr(self.frob_samples), _ptr(self.hstats), _ptr(self.fast_ws), st)
+        self.fold_state(self.state, _cabi.FOLD_MINMAX)
+        self._call("nb200_hist_bins", _ptr(self.samples), n, _cabi.TF_NONE, None, _ptr(self.hist), st)
         self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
         self._call("nb200_hessian_stats_redo", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
-                   sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), _ptr(self.code), st)
-        self.reduce_hstats(self.hstats)
+                   sz, sy, sx, _ptr(self.frob_samples), _ptr(self.hstats), _ptr(self.code), st)
+        self.fold_state(self.state, _cabi.FOLD_BINS)
+        self._call("nb200_finalize_gamma", _ptr(self.hist), _ptr(sp_i), st)
         self._call("nb200_finalize_max_abs", _ptr(self.hstats), _ptr(sp_i), st)
-        self._frob_histogram(sp_i, st)
+        # F5: Frobenius threshold
+        self._call("nb200_hist_reset", _ptr(self.hist), st)
+        if auto_thr:
+            div_ptr = C.c_void_p(sp_i.data_ptr() + 8 * _cabi.SP_MAX_ABS)
+            self._call("nb200_hist_minmax", _ptr(self.frob_samples), n, _cabi.TF_DIV, div_ptr, _ptr(self.hist), st)
+            self.fold_state(self.state, _cabi.FOLD_MINMAX)
+            self._call("nb200_hist_bins", _ptr(self.frob_samples), n, _cabi.TF_DIV, div_ptr, _ptr(self.hist), st)
+            self.fold_state(self.state, _cabi.FOLD_BINS)
         self._call("nb200_finalize_frob_fast", _ptr(self.hist), _ptr(self.hstats), fixed, division, self.max_scale,
                    mask_on, _ptr(sp_i), st)
         if mask_on:
             # emptiness of the mask undecided by the bounds (cut in [0.99, 3.01)): exact max frob^2, gated on sp[AMBIG]
             self._call("nb200_hessian_stats_ambig", _ptr(g), C.byref(own), self._fd_c, self.div_mode, _ptr(sp_i),
-                       sz, sy, sx, _ptr(self.samples), _ptr(self.hstats), st)
-            self.reduce_hstats(self.hstats)
+                       sz, sy, sx, _ptr(self.frob_samples), _ptr(self.hstats), st)
+            self.fold_state(self.state, _cabi.FOLD_MINMAX)
             self._call("nb200_finalize_frob_resolve", _ptr(self.hstats), _ptr(sp_i), st)
         self._call("nb200_frangi_fast", _ptr(g), _ptr(self.acc), C.byref(own), self._fd_c, self.div_mode, a_sq, b_sq,
                    _ptr(sp_i), _ptr(self.diag), st)
@@ -464,13 +488,10 @@ class FrangiEngine3D:
         dst = self.out if out is None else out
         if tuple(dst.shape) != tuple(self.out.shape) or dst.dtype != torch.float32 or not dst.is_contiguous():
             raise ValueError("finalize: out must be a contiguous float32 tensor of the owned-planes shape")
-        if self.nz_buf != self.nz_own:
-            if not hasattr(self, "_out_buf"):
-                self._out_buf = torch.empty_like(self.acc)
-            self._call("nb200_finalize_opening", _ptr(self.acc), _ptr(self._out_buf), C.byref(own), _ptr(self.pct), st)
-            dst.copy_(self._out_buf[self.pad_lo:self.pad_lo + self.nz_own])
-        else:
-            self._call("nb200_finalize_opening", _ptr(self.acc), _ptr(dst), C.byref(own), _ptr(self.pct), st)
+        # the kernel indexes its output like the accumulator (buffer planes) but only writes the planes [zc0, zc1): hand
+        # it the address at which buffer plane 0 WOULD sit, so that the owned planes land in `dst` without a staging copy
+        base = dst.data_ptr() - self.pad_lo * self.ny * self.nx * 4
+        self._call("nb200_finalize_opening", _ptr(self.acc), C.c_void_p(base), C.byref(own), _ptr(self.pct), st)
         return dst
 
     def filter_frame(self, frame: torch.Tensor, apply_mask_volume=True, out=None) -> torch.Tensor:

@@ -122,9 +122,9 @@ class Filter:
     def _allocate_memory(self):
         self.im_memmap = self.im_info.get_memmap(self.im_info.im_path)
         self.shape = self.im_memmap.shape
-        self.frangi_memmap = self.im_info.allocate_memory(
-            self.im_info.pipeline_paths["im_preprocessed"], dtype=self.out_dtype,
-            description="frangi filtered im", return_memmap=True)
+        from .sharding import allocate_shared_output
+        self.frangi_memmap = allocate_shared_output(self.im_info, self.im_info.pipeline_paths["im_preprocessed"],
+                                                    self.out_dtype, "frangi filtered im", self.t_shard)
 
     # ---- device plumbing ------------------------------------------------------------------------
     def _torch_device(self):

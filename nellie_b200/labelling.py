@@ -190,9 +190,9 @@ class Label:
         self.im_memmap = self.im_info.get_memmap(self.im_info.im_path)
         self.frangi_memmap = self.im_info.get_memmap(self.im_info.pipeline_paths["im_preprocessed"])
         self.shape = self.frangi_memmap.shape
-        self.instance_label_memmap = self.im_info.allocate_memory(
-            self.im_info.pipeline_paths["im_instance_label"], dtype="int32",
-            description="instance segmentation", return_memmap=True)
+        from .sharding import allocate_shared_output
+        self.instance_label_memmap = allocate_shared_output(self.im_info, self.im_info.pipeline_paths["im_instance_label"],
+                                                            "int32", "instance segmentation", self.t_shard)
 
     # ---- device plumbing --------------------------------------------------------------------------
     def _torch_device(self):

@@ -6,9 +6,10 @@ Two shardings:
   labelling.py:701-706): frame ``t`` belongs to rank ``t mod G``; no data-path collective.
 * **Z** — one frame split into Z slabs (BASELINE config #3).  Rank g owns planes ``[z0, z1)``.  Per sigma:
   one neighbour halo exchange of ``r_z + 2`` planes of the blurred volume (send/recv, both directions),
-  then the threshold reductions: MAX over ranks of (−min, max) of the sample range, SUM of count + 256
-  bins, MAX of (max|H|, max frob²) — three tiny all-reduces per threshold, stream-ordered, no host round
-  trip.  ``_mask_volume`` all-gathers the ≤ 1e6 lattice samples and exchanges 2 planes of the
+  then the threshold reductions.  The fast path keeps the histogram state and the Hessian stats in one 267-word
+  record and reduces it at five points per sigma with ONE all-gather + one fold kernel each (``fold_state``:
+  MIN / MAX of the sample ranges, SUM of count + 256 bins, MAX of every Hessian-stats word); the exact fallback
+  path still uses the three separate all-reduces.  Everything is stream-ordered, no host round trip.  ``_mask_volume`` all-gathers the ≤ 1e6 lattice samples and exchanges 2 planes of the
   accumulator.  Every rank runs the same kernels on the same global lattice with global border rules,
   so the N-GPU output equals the 1-GPU output bit for bit.
 
@@ -39,6 +40,32 @@ def z_partition(nz: int, world: int) -> List[Tuple[int, int]]:
 def frames_of_rank(num_t: int, rank: int, world: int) -> List[int]:
     """T-sharding: frame t -> rank t mod world."""
     return [t for t in range(int(num_t)) if t % world == rank]
+
+
+def allocate_shared_output(im_info, path, dtype, description, t_shard):
+    """Output file of a T-sharded stage: created by rank 0 ONLY, opened by the others.
+
+    ``im_info.allocate_memory`` (verifier.py:992-1070) re-creates the file (``tifffile.imwrite`` / ``open(path, 'wb')``);
+    if every rank called it, a rank starting later would truncate frames an earlier rank has already written.  Protocol:
+    rank 0 allocates; with an initialised ``torch.distributed`` group all ranks then meet at a barrier and ranks > 0 map
+    the existing file; without a process group (sequential use of the shards in one process) ranks > 0 simply require the
+    file to exist already."""
+    rank, world = (0, 1) if t_shard is None else t_shard
+    use_dist = world > 1 and dist.is_available() and dist.is_initialized()
+    mm = None
+    if rank == 0:
+        mm = im_info.allocate_memory(path, dtype=dtype, description=description, return_memmap=True)
+        if hasattr(mm, "flush"):
+            mm.flush()
+    if use_dist:
+        dist.barrier()
+    if rank != 0:
+        import os
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path}: the output of a T-sharded stage is created by rank 0; run shard (0, {world}) first "
+                                    "or initialise torch.distributed so that the ranks can wait for it")
+        mm = im_info.get_memmap(path)
+    return mm
 
 
 class ZComm:
@@ -96,6 +123,35 @@ class ZComm:
             return
         dist.all_reduce(hstats, op=dist.ReduceOp.MAX, group=self.group)      # float bits of non-negative floats
 
+    def fold_state(self, state: torch.Tensor, stage: int):
+        """One packed reduction point of the threshold state ("pack into <= 2 calls"): all-gather the
+        267-word record [histogram state | Hessian stats] of every rank, then fold the gathered records with the right
+        operator per word — ``stage`` 0: HIST_MIN -> min, HIST_MAX -> max; 1: count + bins -> sum; Hessian stats -> max in
+        both.  One collective + one kernel instead of the three all-reduces (plus slicing glue) of the first version;
+        the result is bit-identical on every rank (integers)."""
+        if self.world == 1:
+            return
+        if getattr(self, "_gath", None) is None or self._gath.device != state.device:
+            self._gath = torch.empty(self.world * state.numel(), dtype=state.dtype, device=state.device)
+        dist.all_gather_into_tensor(self._gath, state, group=self.group)
+        if state.is_cuda:
+            import ctypes as C
+            lib = _cabi.load()
+            _cabi.check(lib.nb200_fold_records(C.c_void_p(self._gath.data_ptr()), self.world, int(stage),
+                                               C.c_void_p(state.data_ptr()),
+                                               C.c_void_p(torch.cuda.current_stream(state.device).cuda_stream)),
+                        "nb200_fold_records")
+            return
+        # host tensors (gloo tests of the plumbing): the same fold with torch ops
+        g = self._gath.view(self.world, state.numel())
+        hw = _cabi.HIST_WORDS
+        if stage == _cabi.FOLD_MINMAX:
+            state[0] = g[:, 0].min()
+            state[1] = g[:, 1].max()
+        else:
+            state[2:hw] = g[:, 2:hw].sum(0)
+        state[hw:] = g[:, hw:].max(0).values
+
     def gather_samples(self, samples: torch.Tensor, n: int):
         """All ranks' lattice samples concatenated (zero padded: consumers keep values > 0 only)."""
         if self.world == 1:
@@ -129,6 +185,7 @@ class ZShardedFilter:
         e.reduce_hist_minmax = self.comm.reduce_hist_minmax
         e.reduce_hist_bins = self.comm.reduce_hist_bins
         e.reduce_hstats = self.comm.reduce_hstats
+        e.fold_state = self.comm.fold_state
         e.gather_samples = self._gather_samples
         self._pinned = None
 
@@ -161,29 +218,3 @@ class ZShardedFilter:
         del full
         torch.cuda.empty_cache()
         return slab
-
-    def e2e(self, steps: int, slab: torch.Tensor):
-        """Whole-job voxels/s through pinned host buffers (H2D + filter + D2H per step), max over ranks."""
-        import time
-        host_in = torch.empty(slab.shape, dtype=torch.float32).pin_memory()
-        host_in.copy_(slab)
-        host_out = torch.empty(slab.shape, dtype=torch.float32).pin_memory()
-        staging = torch.empty_like(slab)
-
-        def step():
-            staging.copy_(host_in, non_blocking=True)
-            out = self.engine.filter_frame(staging)
-            host_out.copy_(out, non_blocking=True)
-
-        step()
-        torch.cuda.synchronize(self.device)
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            step()
-        torch.cuda.synchronize(self.device)
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=self.device)
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        voxels = float(self.shape[0]) * self.shape[1] * self.shape[2]
-        return {"value": voxels * steps / float(dt.item()), "unit": "voxels/s",
-                "h2d_bytes_per_step": int(voxels * 4), "d2h_bytes_per_step": int(voxels * 4)}

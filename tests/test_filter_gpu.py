@@ -320,20 +320,44 @@ def test_t_sharded_runs_fill_the_same_output(tmp_path):
     f0.run()                                                   # allocates the output file and fills frames 0, 2, 4
     pre = imio.memmap_ome_tiff(shard.pipeline_paths["im_preprocessed"], "r")
     assert pre[0].any() and not pre[1].any() and pre[2].any()
-    f1 = Filter(shard, device="b200", t_shard=(1, 2))
-    f1._get_t(); f1._set_default_sigmas()
-    f1.im_memmap = shard.get_memmap(shard.im_path)
-    f1.frangi_memmap = shard.get_memmap(shard.pipeline_paths["im_preprocessed"])   # rank > 0 opens, does not re-create
-    f1._run_filter()
+    Filter(shard, device="b200", t_shard=(1, 2)).run()         # rank > 0 maps the existing file, never re-creates it
     assert np.array_equal(imio.read_tiff(shard.pipeline_paths["im_preprocessed"]),
                           imio.read_tiff(full.pipeline_paths["im_preprocessed"]))
     l0 = Label(shard, device="b200", t_shard=(0, 2))
     l0.run()
-    l1 = Label(shard, device="b200", t_shard=(1, 2))
-    l1._get_t()
-    l1.im_memmap = shard.get_memmap(shard.im_path)
-    l1.frangi_memmap = shard.get_memmap(shard.pipeline_paths["im_preprocessed"])
-    l1.instance_label_memmap = shard.get_memmap(shard.pipeline_paths["im_instance_label"])
-    l1._run_segmentation()
+    Label(shard, device="b200", t_shard=(1, 2)).run()
     assert np.array_equal(imio.read_tiff(shard.pipeline_paths["im_instance_label"]),
                           imio.read_tiff(full.pipeline_paths["im_instance_label"]))
+
+
+def _t_shard_rank(rank, world, port, info):
+    import os
+    import torch.distributed as dist
+    from nellie_b200 import Filter, Label
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        Filter(info, device="b200", t_shard=(rank, world)).run()
+        dist.barrier()                                         # Label reads frames the other rank filtered
+        Label(info, device="b200", t_shard=(rank, world)).run()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_t_sharded_run_in_two_processes(tmp_path):
+    """Two PROCESSES call run() on the same files with t_shard=(rank, 2) (what torchrun launches): rank 0 creates the
+    outputs, rank 1 waits at the barrier and maps them; nothing is truncated, the result equals the unsharded run."""
+    import socket
+    import torch.multiprocessing as mp
+    from nellie_b200 import Filter, Label, imio
+    from nellie_b200.phantoms import tubular_phantom_np
+    dim_res = {"X": 0.1, "Y": 0.1, "Z": 0.2, "T": 1.0}
+    frames = np.stack([tubular_phantom_np((16, 40, 64), seed=950 + t, n_tubes=4) for t in range(6)])
+    full = imio.StackInfo.from_array(frames, "TZYX", dim_res, str(tmp_path / "full"), "p")
+    Filter(full, device="b200").run()
+    Label(full, device="b200").run()
+    shard = imio.StackInfo.from_array(frames, "TZYX", dim_res, str(tmp_path / "shard"), "p")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_t_shard_rank, args=(2, port, shard), nprocs=2, join=True)
+    for key in ("im_preprocessed", "im_instance_label"):
+        assert np.array_equal(imio.read_tiff(shard.pipeline_paths[key]), imio.read_tiff(full.pipeline_paths[key])), key

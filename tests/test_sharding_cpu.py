@@ -55,6 +55,24 @@ def _worker(rank, world, port, nz, halo, out_dir):
         comm.reduce_hstats(hs)
         assert int(hs[0]) == int(np.float32(1.5 + world - 1).view(np.uint32))
         assert int(hs[1]) == int(np.float32(9.0).view(np.uint32))
+        # packed record [histogram state | Hessian stats]: one all-gather + fold per reduction point (fast path)
+        from nellie_b200 import _cabi
+        rec = torch.zeros(_cabi.STATE_WORDS, dtype=torch.int64)
+        hw = _cabi.HIST_WORDS
+        rec[0] = 1000 + 10 * rank if rank != 1 else 0xFFFFFFFF
+        rec[1] = 5000 + rank if rank != 1 else 0
+        rec[2] = 3 * (rank + 1) if rank != 1 else 0
+        rec[3:hw] = rank + 1 if rank != 1 else 0
+        rec[hw:] = torch.arange(_cabi.HS_WORDS) * 7 + rank
+        before = rec.clone()
+        comm.fold_state(rec, _cabi.FOLD_MINMAX)
+        assert int(rec[0]) == min(1000 + 10 * r for r in contributing) and int(rec[1]) == max(5000 + r for r in contributing)
+        assert torch.equal(rec[2:hw], before[2:hw]), "stage 0 must not touch count / bins"
+        assert torch.equal(rec[hw:], torch.arange(_cabi.HS_WORDS) * 7 + world - 1)
+        comm.fold_state(rec, _cabi.FOLD_BINS)
+        assert int(rec[2]) == sum(3 * (r + 1) for r in contributing)
+        assert bool((rec[3:hw] == sum(r + 1 for r in contributing)).all())
+        assert int(rec[0]) == min(1000 + 10 * r for r in contributing), "stage 1 must not touch min / max"
         # lattice samples: ragged lengths, zero padded
         n = 4 + rank
         s = torch.arange(1, n + 1, dtype=torch.float32) + 100 * rank
