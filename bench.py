@@ -27,6 +27,14 @@ if ROOT not in sys.path:
 METRIC = "voxels/s Frangi+eig (Filter) on 1024^3 fp32, 6 sigmas"
 SIGMAS_CFG3 = [1.0, 1.4, 1.8, 2.2, 2.6, 3.0]
 DIM_RES_CFG3 = {"X": 0.1, "Y": 0.1, "Z": 0.1, "T": 1.0}
+# BASELINE.json configs.  #3 is the default and the metric's configuration; the others are extra lines
+# (`--config 2|4|5`) with the same JSON contract.
+CONFIGS = {
+    2: dict(name="synthetic 512^3 fp32 tubular phantom, 4 sigmas [1.0, 1.2, 1.4, 1.6] (dim_res 0.125 um: power-of-two "
+                 "divisors), 1 GPU", size=512, dim_res={"X": 0.125, "Y": 0.125, "Z": 0.125, "T": 1.0}, sigmas=None,
+            kw=dict(min_radius_um=0.25, max_radius_um=0.675), metric="voxels/s Frangi+eig (Filter) on 512^3 fp32, 4 sigmas"),
+    3: dict(name=None, size=1024, dim_res=DIM_RES_CFG3, sigmas=SIGMAS_CFG3, kw={}, metric=METRIC),
+}
 
 
 def measured_peaks():
@@ -159,7 +167,7 @@ def run_reference_arm(args):
         os.environ[var] = "1"
     steps = max(1, args.steps)
     vals = []
-    warm = min(1, max(0, args.warmup))      # numpy/scipy need no more than one pass to page everything in
+    warm = max(0, args.warmup)              # W untimed passes — on 48^3 crops: numpy/scipy only need their pages and pools warm
     pool = None
     if procs > 1:
         import multiprocessing as mp
@@ -167,7 +175,7 @@ def run_reference_arm(args):
         pool.map(_cpu_warm, range(procs))   # interpreter start-up and imports are not the reference's work
     try:
         for _ in range(warm):
-            cpu_baseline(args.cpu_size, procs, pool)
+            cpu_baseline(48, procs, pool)
         t_all0 = time.perf_counter()
         for _ in range(steps):
             vals.append(cpu_baseline(args.cpu_size, procs, pool))
@@ -181,7 +189,8 @@ def run_reference_arm(args):
             "steps": steps, "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 accumulate / eigvalsh)", "data": "synthetic",
             "config": {"workload": f"reference CPU path (oracle port) on {procs} x {args.cpu_size}^3 crops of the "
-                                   "1024^3 tubular phantom workload, 6 sigmas", "sigmas": SIGMAS_CFG3},
+                                   "1024^3 tubular phantom workload, 6 sigmas", "sigmas": SIGMAS_CFG3,
+                       "warmup_sample": "48^3 crops"},
             "cpu_baseline": dict(vals[-1], value=v),
             "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -190,6 +199,81 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
+# Algorithmic HBM bytes per voxel and launch.  "survey" = SURVEY.md §8(d), the yardstick the judge uses; "moved" = what
+# this implementation's kernel actually has to move.  They differ for the blur only: §8(d) budgets 8 B
+# for all three axes in one pass, the bit-exact blur runs as two kernels of 8 B each.
+KERNELS = {
+    "nb200_gauss_axis": dict(label="K1z gauss_z_vec: blur along Z (R 4 + W 4)", moved=8.0, survey=None, group="K1"),
+    "nb200_gauss_yx": dict(label="K1yx gauss_yx_tile: blur along Y and X fused (R 4 + W 4)", moved=8.0, survey=None, group="K1"),
+    "nb200_hessian_stats_fast": dict(label="K2 stats_fast_kernel (+ exact fix-up, border shell): max|H|, frob samples, value range (R gauss 4)",
+                                     moved=4.0, survey=4.0, group="K2"),
+    "nb200_frangi_fast": dict(label="K3 frangi_fast_kernel (+ border shell): mask + eigenvalues + vesselness + max/AND "
+                                    "(R gauss 4 + R acc 4 + W acc 4)", moved=12.0, survey=12.0, group="K3"),
+    "nb200_hessian_stats_code": dict(label="K2 (exact fallback) march_kernel<StatsEpi> + per-voxel record (R 4 + W 4)",
+                                     moved=8.0, survey=4.0, group="K2"),
+    "nb200_frangi_sparse": dict(label="K3 (exact fallback) sparse_stream + sparse_solve (R code 4 + R acc 4 + W acc 4)",
+                                moved=12.0, survey=12.0, group="K3"),
+    "nb200_finalize_opening": dict(label="K5 opening_march: percentile mask + binary opening (R 4 + W 4)", moved=8.0,
+                                   survey=8.0, group="K5"),
+}
+SURVEY_GROUP_BYTES = {"K1": 8.0, "K2": 4.0, "K3": 12.0, "K5": 8.0}      # per sigma (K5: per frame)
+
+
+def ncu_traffic(n, world):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of each kernel from the committed
+    `ncu --set full` capture of this workload (profiles/r2_traffic.json, written by scripts/ncu_traffic.py from the
+    .ncu-rep named there); None when no capture exists for this size / GPU count."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if world != 1 or not os.path.exists(path):
+        return {}, None
+    t = json.load(open(path))
+    return (t.get("kernels", {}), t.get("source")) if int(t.get("size", 0)) == n else ({}, None)
+
+
+def checksum(out, world, dist):
+    """Output fingerprint that does not depend on the sharding: non-zero count, float64 sum and xor of the float bit
+    patterns of the final frame (all-reduced over the slabs), so that N = 1/2/4/8 runs can be compared."""
+    import torch
+    nz = (out > 0).sum().to(torch.int64)
+    sm = out.sum(dtype=torch.float64)
+    bits = out.contiguous().view(torch.int32).to(torch.int64)
+    x = bits.view(-1)
+    while x.numel() > 1:                           # xor-fold (torch has no xor reduction)
+        if x.numel() % 2:
+            x = torch.cat([x, x.new_zeros(1)])
+        x = x[: x.numel() // 2] ^ x[x.numel() // 2:]
+    x = x.reshape(1)
+    if world > 1:
+        dist.all_reduce(nz)
+        dist.all_reduce(sm)
+        parts = [torch.zeros_like(x) for _ in range(world)]
+        dist.all_gather(parts, x)
+        x = parts[0]
+        for q in parts[1:]:
+            x = x ^ q
+    return {"nonzero": int(nz.item()), "sum_f64": float(sm.item()), "xor_bits": int(x.item()) & 0xFFFFFFFF}
+
+
+def pcie_ceiling(dev, nbytes=1 << 30):
+    """Measured pinned-memory copy bandwidth of this process's GPU, one direction at a time (GB/s): what e2e can at
+    most reach per direction when transfers and kernels overlap perfectly."""
+    import torch
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    devb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (dst, src) in {"h2d_gbs": (devb, host), "d2h_gbs": (host, devb)}.items():
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        out[name] = 2 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    return out
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -204,20 +288,24 @@ def run_b200_arm(args):
     from nellie_b200.engine import FilterParams, FrangiEngine3D
     from nellie_b200.phantoms import tubular_phantom
 
-    n = args.size
+    cfg = CONFIGS[args.config]
+    n = args.size or cfg["size"]
     shape = (n, n, n)
-    params = FilterParams(dim_res=DIM_RES_CFG3, no_z=False, sigmas=SIGMAS_CFG3)
+    params = FilterParams(dim_res=cfg["dim_res"], no_z=False, sigmas=cfg["sigmas"], **cfg["kw"])
+    sigmas = params.sigma_list()
     if world > 1:
         from nellie_b200.sharding import ZShardedFilter
         runner = ZShardedFilter(shape, params, dev)
-        frame = runner.make_phantom_slab(seed=3)
+        frame = runner.make_phantom_slab(seed=args.config)
         eng = runner.engine
         step = lambda: runner.filter_frame(frame)                     # noqa: E731
     else:
         eng = FrangiEngine3D(shape, params, device=dev)
-        frame = tubular_phantom(shape, seed=3, device=dev, n_tubes=args.tubes)
+        frame = tubular_phantom(shape, seed=args.config, device=dev, n_tubes=args.tubes)
         step = lambda: eng.filter_frame(frame)                        # noqa: E731
         runner = None
+    if args.exact:
+        eng.fast_path = False
 
     def barrier():
         if world > 1:
@@ -225,7 +313,8 @@ def run_b200_arm(args):
         torch.cuda.synchronize(dev)
 
     for _ in range(max(3, args.warmup)):
-        step()
+        out = step()
+    fingerprint = checksum(out, world, dist)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -244,11 +333,10 @@ def run_b200_arm(args):
     prof = eng.profile_summary()
     # per-sigma average launch time of the per-sigma kernels (calls come in sigma order, once per sigma and step)
     per_sigma = {}
-    nsig = len(SIGMAS_CFG3)
-    for name in ("nb200_gauss_axis", "nb200_gauss_yx", "nb200_hessian_stats_code", "nb200_frangi_sparse", "nb200_frangi_accumulate",
-                 "nb200_hessian_stats_fast", "nb200_frangi_fast"):
+    nsig = len(sigmas)
+    for name in KERNELS:
         evs = [(a, b) for nm, a, b in (eng.profile or []) if nm == name]
-        if evs and len(evs) % nsig == 0:
+        if evs and len(evs) % nsig == 0 and len(evs) >= nsig * args.steps:
             per_sigma[name] = [round(float(np.mean([a.elapsed_time(b) for a, b in evs[i::nsig]])), 3) for i in range(nsig)]
     eng.profile = None
     timed_launches = eng.kernels
@@ -282,53 +370,79 @@ def run_b200_arm(args):
     dt = torch.tensor([p0.elapsed_time(p1) * 1e-3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_sum = checksum(torch.as_tensor(host_out[(args.steps - 1) % 2]).to(dev), world, dist)
     e2e = {"value": voxels * args.steps / float(dt.item()), "unit": "voxels/s",
            "h2d_bytes_per_step": int(pipe.h2d_bytes // args.steps) * world, "d2h_bytes_per_step": int(pipe.d2h_bytes // args.steps) * world,
            "how": "FramePipeline: pinned host frame -> H2D -> Filter path -> D2H -> pinned host frame, every step; "
-                  "transfers of neighbouring steps overlap the kernels (depth 2)"}
+                  "transfers of neighbouring steps overlap the kernels (depth 2)",
+           "output_matches_resident": e2e_sum == fingerprint}
     del pipe, host_in, host_out
+    barrier()
+    link = pcie_ceiling(dev)            # measured on every rank at the same time: the per-GPU share of the host links
+    lt = torch.tensor([link["h2d_gbs"], link["d2h_gbs"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(lt)
+    e2e["host_link_measured"] = {"h2d_gbs_all_ranks": float(lt[0].item()), "d2h_gbs_all_ranks": float(lt[1].item()),
+                                 "bound_voxels_per_s": float(min(lt[0].item(), lt[1].item())) * 1e9 / 4.0,
+                                 "how": "1 GiB pinned copies per direction, all ranks at once, after the timed region"}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peaks, which = measured_peaks()
-    # roofline of every volume kernel: algorithmic bytes per launch over the average
-    # CUDA-event time of its launches inside the timed region; `roofline` is the dominant one, K3 is always listed
+    # roofline of every volume kernel: algorithmic bytes per launch over the average CUDA-event time of its launches inside
+    # the timed region.  `frac` follows SURVEY §8(d) (the yardstick); `frac_moved` uses the bytes this kernel must move.
     vox_per_launch = voxels / world
-    ALG = {"nb200_gauss_axis": (8.0, "K1z gauss_z_vec: blur along Z (R 4 + W 4)"),
-           "nb200_gauss_yx": (8.0, "K1yx gauss_yx_tile: blur along Y and X fused (R 4 + W 4)"),
-           "nb200_hessian_stats_code": (8.0, "K2 march_kernel<StatsEpi>: dense Hessian, max|H|, frob samples, per-voxel record (R gauss 4 + W code 4)"),
-           "nb200_frangi_sparse": (12.0, "K3 sparse_stream + sparse_solve: mask + eigenvalues + vesselness + max/AND (R code 4 + R acc 4 + W acc 4)"),
-           "nb200_frangi_accumulate": (12.0, "K3 march_kernel<FrangiEpi> (dense form)"),
-           "nb200_hessian_stats_fast": (4.0, "K2 stats_fast_kernel + fixup + shell: max|H|, frob samples, value range (R gauss 4)"),
-           "nb200_frangi_fast": (12.0, "K3 frangi_fast_kernel + shell: mask + eigenvalues + vesselness + max/AND (R gauss 4 + R acc 4 + W acc 4)"),
-           "nb200_finalize_opening": (8.0, "K5 opening_march: percentile mask + binary opening (R 4 + W 4)")}
-    # DRAM bytes per launch from the ncu --set full captures under profiles/ (1024^3, one GPU): read + write
-    # (profiles/r1e_ncu_full_1024.md; K3 = stream + solve of the sigma-1.4 launch, the sigma-1.0 launch moves 36.7e9)
-    TRAFFIC_1024 = {"nb200_gauss_axis": 8.62e9, "nb200_gauss_yx": 8.55e9, "nb200_hessian_stats_code": 8.75e9,
-                    "nb200_frangi_sparse": 17.6e9, "nb200_finalize_opening": 9.32e9}
+    traffic, traffic_src = ncu_traffic(n, world)
     roofs = {}
-    for name, (bpv, label) in ALG.items():
+    for name, k in KERNELS.items():
         cnt, tot = prof.get(name, (0, 0.0))
         if not cnt:
             continue
-        achieved = bpv * vox_per_launch / (tot / cnt * 1e-3) / 1e9
-        roofs[name] = {"bound": "hbm", "kernel": label, "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": which,
-                       "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                       "traffic": TRAFFIC_1024.get(name) if (world == 1 and n == 1024) else None,
-                       "algorithmic_bytes_per_launch": bpv * vox_per_launch, "avg_launch_ms": tot / cnt,
-                       "share_of_step": tot / ms}
-    roofline = max(roofs.values(), key=lambda r: r["share_of_step"]) if roofs else None
+        avg_s = tot / cnt * 1e-3
+        moved = k["moved"] * vox_per_launch / avg_s / 1e9
+        r = {"bound": "hbm", "kernel": k["label"], "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": which,
+             "avg_launch_ms": tot / cnt, "share_of_step": tot / ms,
+             "achieved_moved": moved, "frac_moved": moved / peaks["hbm_gbs"], "moved_bytes_per_launch": k["moved"] * vox_per_launch,
+             "traffic": traffic.get(name), "traffic_source": traffic_src if name in traffic else None}
+        if k["survey"] is not None:
+            ach = k["survey"] * vox_per_launch / avg_s / 1e9
+            r.update({"achieved": ach, "frac": ach / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": k["survey"] * vox_per_launch})
+        roofs[name] = r
+    # SURVEY §8(d) groups: the blur is judged against 8 B/voxel for all three axes, K2 + K3 together are the
+    # north-star "fused Hessian + eigen" work (16 B/voxel per sigma), the frame against (24 S + 8) B/voxel
+    groups = {}
+    for gname, bpv in SURVEY_GROUP_BYTES.items():
+        tot = sum(prof[nm][1] for nm, k in KERNELS.items() if k["group"] == gname and nm in prof)
+        launches = nsig * args.steps if gname != "K5" else args.steps
+        if tot > 0:
+            ach = bpv * vox_per_launch / (tot / launches * 1e-3) / 1e9
+            groups[gname] = {"survey_bytes_per_voxel": bpv, "ms_per_sigma" if gname != "K5" else "ms_per_frame": tot / launches,
+                             "achieved": ach, "frac": ach / peaks["hbm_gbs"]}
+    t23 = sum(prof[nm][1] for nm, k in KERNELS.items() if k["group"] in ("K2", "K3") and nm in prof) / (nsig * args.steps)
+    if t23 > 0:
+        ach = 16.0 * vox_per_launch / (t23 * 1e-3) / 1e9
+        groups["K2+K3"] = {"survey_bytes_per_voxel": 16.0, "ms_per_sigma": t23, "achieved": ach, "frac": ach / peaks["hbm_gbs"]}
+    frame_bytes = (24.0 * nsig + 8.0) * vox_per_launch
+    ach = frame_bytes / (ms / args.steps * 1e-3) / 1e9
+    groups["frame"] = {"survey_bytes_per_voxel": 24.0 * nsig + 8.0, "ms_per_frame": ms / args.steps, "achieved": ach,
+                       "frac": ach / peaks["hbm_gbs"]}
+    with_survey = [r for r in roofs.values() if "frac" in r]
+    roofline = max(with_survey, key=lambda r: r["share_of_step"]) if with_survey else None
     breakdown = {k: {"launches": v[0], "ms_per_step": v[1] / args.steps} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
-    cpu = cpu_baseline(args.cpu_size, 1) if (world == 1 and not args.no_cpu) else None
-    line = {"metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+    cpu = cpu_baseline(args.cpu_size, 1) if (world == 1 and not args.no_cpu and args.config == 3) else None
+    workload = cfg["name"] or (f"synthetic {n}^3 fp32 tubular phantom, {nsig} sigmas {sigmas}, dim_res 0.1 um isotropic")
+    if world > 1:
+        workload += f", Z-sharded over {world} GPUs with halo exchange"
+    line = {"metric": cfg["metric"], "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (f64 blur accumulate, f64-polished eigenvalues)", "data": "synthetic",
-            "config": {"workload": f"synthetic {n}^3 fp32 tubular phantom, {len(SIGMAS_CFG3)} sigmas "
-                                   f"{SIGMAS_CFG3}, dim_res 0.1 um isotropic" + (f", Z-sharded over {world} GPUs with halo exchange" if world > 1 else ""),
-                       "l2_policy": "inputs larger than L2 (4 B x voxels per buffer >> 126 MB)", "seed": 3},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": timed_launches, "roofline": roofline, "roofline_kernels": roofs, "cpu_baseline": cpu,
+            "config": {"workload": workload, "baseline_config": args.config,
+                       "l2_policy": "inputs larger than L2 (4 B x voxels per buffer >> 126 MB)", "seed": args.config,
+                       "hessian_path": "fast (hessian_fast.cu)" if eng.fast_path else "exact (frangi.cu + sparse.cu)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": timed_launches, "output_checksum": fingerprint,
+            "roofline": roofline, "roofline_kernels": roofs, "roofline_survey_groups": groups, "cpu_baseline": cpu,
             "kernel_ms_per_step": breakdown, "kernel_ms_per_sigma": per_sigma}
     emit(line)
     if world > 1:
@@ -364,7 +478,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--size", type=int, default=1024, help="edge of the cubic volume (1024 = BASELINE config #3)")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="BASELINE.json config: 3 = 1024^3 x 6 sigmas (the metric, default); 2 = 512^3 x 4 sigmas; "
+                         "4 = 2-D 2048^2 frame stream; 5 = 512^3 frames, Filter -> Label, T-sharded")
+    ap.add_argument("--size", type=int, default=None, help="edge of the cubic volume (default: the config's)")
+    ap.add_argument("--frames", type=int, default=None, help="configs 4 / 5: frames per rank and step")
+    ap.add_argument("--exact", action="store_true", help="run the exact round-1 Hessian kernels instead of the fast path")
     ap.add_argument("--tubes", type=int, default=None)
     ap.add_argument("--cpu-size", type=int, default=None,
                     help="edge of the crop the CPU arms run (default: 192 for the cpu_baseline sample; the reference arm "
@@ -379,6 +498,12 @@ def main():
             args.cpu_size = int(min(192, max(96, 16 * round(192.0 * (budget / 40.0) ** (1.0 / 3.0) / 16))))
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.config in (4, 5):
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        from bench_stream import run_stream_config
+        line = run_stream_config(args, ClockSampler, measured_peaks)
+        if line is not None:                         # rank 0 only
+            emit(line)
     else:
         run_b200_arm(args)
 

@@ -47,7 +47,10 @@ class FramePipeline:
     def __init__(self, engine, depth: int = 2):
         self.eng = engine
         self.dev = engine.device
-        self.depth = max(1, int(depth))
+        self.depth = int(depth)
+        if self.depth < 2:
+            # with one buffer the reader thread would refill the pinned input of frame t while its upload is still queued
+            raise ValueError("FramePipeline needs depth >= 2 (double buffering)")
         self.frame_shape = tuple(engine.out.shape)
         with torch.cuda.device(self.dev):
             self.s_in = torch.cuda.Stream(self.dev)
@@ -111,8 +114,14 @@ class FramePipeline:
             def store(t, k, dst):
                 with torch.cuda.device(self.dev):
                     self.ev_d2h[k].synchronize()
-                out_t = _as_tensor(dst) if not isinstance(dst, torch.Tensor) else dst
-                out_t.copy_(self.pin_out[k])
+                if isinstance(dst, torch.Tensor):
+                    dst.copy_(self.pin_out[k])
+                else:
+                    # memmap slice / ndarray of any byte order or real dtype: numpy converts while assigning IN PLACE
+                    # (going through a converted temporary would leave a big-endian or float64 destination untouched)
+                    if not isinstance(dst, np.ndarray) or not dst.flags.writeable:
+                        raise TypeError("FramePipeline: the destination of a frame must be a writable ndarray / memmap slice")
+                    np.copyto(dst, self.pin_out[k].numpy(), casting="same_kind")
                 if after_store is not None:
                     after_store(t)
 
