@@ -150,9 +150,12 @@ int nb200_finalize_frob(const long long* state, const long long* hstats, double 
                         double division, double* sp, void* stream);
 /* max|H| -> sp[MAX_ABS] (must run before hist_* with NB200_TF_DIV on &sp[MAX_ABS]) */
 int nb200_finalize_max_abs(const long long* hstats, double* sp, void* stream);
-/* Label threshold (labelling.py:440-455): out[0] = min(10**tri, 10**otsu) as float32 value,
- * out[1] = 10**tri, out[2] = 10**otsu, out[3] = 1 if no samples (None), out[4] = status.
- * With log_domain = 0 it is the plain Otsu of labelling.py:457-465 (out[0] = otsu). */
+/* Label threshold (labelling.py:440-455): out (device double[7]): out[0] = min(10**tri, 10**otsu) as float32 value,
+ * out[1] = 10**tri, out[2] = 10**otsu (float64 pow rounded once to float32), out[3] = 1 if no samples (None),
+ * out[4] = status, out[5] / out[6] = triangle / Otsu threshold in the histogram's own domain (log10): a host caller
+ * that wants the reference's bits applies `10 ** np.float32(.)` to these itself (numpy's scalar float32 power is
+ * libm powf, which is not correctly rounded for ~0.05 % of arguments).  The samples are transformed with numpy's own
+ * float32 log10 (devmath.cuh np_log10f).  With log_domain = 0 it is the plain Otsu of labelling.py:457-465. */
 int nb200_finalize_label_threshold(const long long* state, int log_domain, double* out, void* stream);
 
 /* ---- F4: Hessian statistics -------------------------------------------------------------
@@ -289,7 +292,7 @@ int nb200_log2d_combine(const float* acc, const float* L, long long n, long long
  * threshold (strict >, optional intensity gate on `raw`) -> fill holes (3-D only) -> 26-/8-connected
  * components -> drop components smaller than min_area -> 3^d majority smoothing -> components again.
  * labels: int32, 0 = background, ids 1..n in raster order of each component's first voxel
- * (scipy.ndimage.label numbering).  thr: device double[5] as written by
+ * (scipy.ndimage.label numbering).  thr: device double[>= 5] as written by
  * nb200_finalize_label_threshold (thr[0] = threshold, thr[3] != 0 -> "None": empty mask).
  * nz = 1 selects the 2-D path.  workspace: nb200_label_workspace_bytes() bytes of device memory.
  * n_labels: device int64 receiving the component count. */

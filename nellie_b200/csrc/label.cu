@@ -150,6 +150,9 @@ ccl_merge_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dim
     for (long long base = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); base < d.total; base += stride) {
         const long long i = base + lane;
         const bool valid = i < d.total && mask[i] == want;
+        // a 32-voxel strip without a member of the set has nothing to link (every test below starts from `valid`):
+        // the foreground of a frangi frame is a few percent of the voxels, so most strips end here
+        if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
         int z = 0, y = 0, x = 0;
         if (valid) {
             z = (int)(i / d.plane);
@@ -242,26 +245,44 @@ area_keep_kernel(Dims d, const int* __restrict__ parent, const int* __restrict__
 }
 
 // ---- 3^d majority with reflected borders -----------------------------------------------------------
+// One warp per 32-voxel strip of a row: each lane loads its own byte of the 9 (3 in 2-D) neighbouring rows, the
+// horizontal neighbours come from shuffles (the strip's two outer columns from one extra load each), and a strip
+// whose rows hold no set voxel at all is left after the loads (the smoothed mask is zero there).
 __global__ void __launch_bounds__(THREADS)
 majority_kernel(const unsigned char* __restrict__ in, Dims d, unsigned char* __restrict__ out) {
     const int need = d.nz > 1 ? 14 : 5;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int z = (int)(i / d.plane);
-        const long long rem = i - (long long)z * d.plane;
-        const int y = (int)(rem / d.nx), x = (int)(rem - (long long)y * d.nx);
+    const int wpr = (d.nx + 31) / 32;
+    const long long nwin = (long long)d.nz * d.ny * wpr;
+    const int lane = threadIdx.x & 31;
+    const int dz0 = d.nz > 1 ? -1 : 0, dz1 = d.nz > 1 ? 1 : 0;
+    for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < nwin;
+         w += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const long long row = w / wpr;
+        const int x0 = (int)(w - row * wpr) * 32, x = x0 + lane;
+        const int z = (int)(row / d.ny), y = (int)(row - (long long)z * d.ny);
+        const int xc = min(x, d.nx - 1);                       // lanes beyond the row read its last voxel, never store
+        const int xl = max(x0 - 1, 0), xr = min(x0 + 32, d.nx - 1);   // reflect of a 1-voxel overhang = clamp
         int cnt = 0;
-        const int dz0 = d.nz > 1 ? -1 : 0, dz1 = d.nz > 1 ? 1 : 0;
+        unsigned any = 0u;
         for (int dz = dz0; dz <= dz1; ++dz) {
-            const int zz = min(max(z + dz, 0), d.nz - 1);      // reflect of a 1-voxel overhang = clamp
+            const int zz = min(max(z + dz, 0), d.nz - 1);
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
                 const int yy = min(max(y + dy, 0), d.ny - 1);
-                const unsigned char* row = in + (long long)zz * d.plane + (long long)yy * d.nx;
-                cnt += row[max(x - 1, 0)] + row[x] + row[min(x + 1, d.nx - 1)];
+                const unsigned char* r = in + (long long)zz * d.plane + (long long)yy * d.nx;
+                const int c = r[xc];
+                // outer columns of the strip: lane 0 needs x0-1, the last valid lane needs its right neighbour
+                const int edge = lane == 0 ? r[xl] : (lane == 31 ? r[xr] : 0);
+                int left = __shfl_up_sync(0xffffffffu, c, 1), right = __shfl_down_sync(0xffffffffu, c, 1);
+                if (lane == 0) left = edge;
+                if (lane == 31) right = edge;
+                if (x == d.nx - 1) right = c;                  // clamp at the end of the row (x+1 -> x)
+                if (x == 0) left = c;
+                cnt += left + c + right;
+                any |= __ballot_sync(0xffffffffu, (c | edge) != 0);
             }
         }
-        out[i] = cnt >= need ? 1 : 0;
+        if (x < d.nx) out[row * d.nx + x] = (any != 0u && cnt >= need) ? 1 : 0;
     }
 }
 

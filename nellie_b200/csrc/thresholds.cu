@@ -54,7 +54,7 @@ __device__ __forceinline__ bool transformed(float raw, int tf, float divisor, fl
         return true;
     }
     if (!(raw > 0.0f)) return false;
-    out = (tf == NB200_TF_LOG10) ? log10f(raw) : raw;
+    out = (tf == NB200_TF_LOG10) ? nb::np_log10f(raw) : raw;   // numpy float32 log10, bit-exact (devmath.cuh)
     return true;
 }
 
@@ -446,10 +446,12 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_label_kernel(const long 
     TwoThresholds t;
     if (have) t = otsu_triangle(state, work);
     if (threadIdx.x != 0) return;
-    out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; out[3] = 1.0; out[4] = 0.0;
+    out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; out[3] = 1.0; out[4] = 0.0; out[5] = 0.0; out[6] = 0.0;
     if (!have) return;
     out[3] = 0.0;
     out[4] = (double)t.status;
+    out[5] = (double)t.tri;        // the thresholds in the domain of the histogram (log10 for the frangi threshold):
+    out[6] = (double)t.otsu;       // the host applies 10 ** np.float32(.) itself, exactly as labelling.py:452-455 does
     if (log_domain) {
         // 10 ** np.float32 -> float32 power; evaluate in f64 and round once (labelling.py:452-455)
         const float a = (float)pow(10.0, (double)t.tri);

@@ -60,7 +60,7 @@ class LabelEngine:
         n_samp = (self.n + self.step - 1) // self.step
         self.samples = torch.empty(max(1, n_samp), dtype=torch.float32, device=dev)
         self.hist = torch.zeros(_cabi.HIST_WORDS, dtype=torch.int64, device=dev)
-        self.thr = torch.zeros(5, dtype=torch.float64, device=dev)
+        self.thr = torch.zeros(7, dtype=torch.float64, device=dev)
         self.launches = 0
 
     def _call(self, name, *args):
@@ -104,7 +104,11 @@ class LabelEngine:
             return None
         if out[4] != 0.0:
             raise ValueError("attempt to get argmax of an empty sequence")  # what the reference raises
-        return float(np.float32(out[0]))
+        # labelling.py:452-455 on the two scalars themselves: ``10 ** np.float32`` is numpy's scalar float32 power (libm
+        # powf); doing it here reproduces its bits on any host, which a device pow could only approximate
+        triangle = 10 ** np.float32(out[5])
+        otsu = 10 ** np.float32(out[6])
+        return float(min(triangle, otsu))
 
     def intensity_otsu(self, raw_f32):
         """labelling.py:457-465 (float32 arithmetic; exact for float32 inputs)."""
@@ -290,7 +294,8 @@ class Label:
         buf = bufs.get(slot)
         if buf is None or buf.shape != src.shape or buf.dtype != src.dtype:
             buf = bufs[slot] = torch.empty(src.shape, dtype=src.dtype).pin_memory()
-        buf.copy_(src)
+        from .pipeline import parallel_copyto
+        parallel_copyto(buf.numpy(), src.numpy())
         t = buf.to(self._torch_device(), non_blocking=True)
         return t if t.dtype == torch.float32 else t.to(torch.float32)
 
@@ -316,7 +321,8 @@ class Label:
                 if host is None or host.shape != labels.shape:
                     host = bufs["labels"] = torch.empty(labels.shape, dtype=torch.int32).pin_memory()
                 host.copy_(labels)
-            self.instance_label_memmap[t, ...] = host.numpy()
+            from .pipeline import parallel_copyto
+            parallel_copyto(self.instance_label_memmap[t, ...], host.numpy())
             if (t + 1) % self.flush_interval == 0 and hasattr(self.instance_label_memmap, "flush"):
                 self.instance_label_memmap.flush()
         if hasattr(self.instance_label_memmap, "flush"):

@@ -24,6 +24,26 @@ import numpy as np
 import torch
 
 
+_COPY_POOL = None
+
+
+def parallel_copyto(dst: np.ndarray, src: np.ndarray, threads: int = 8, min_bytes: int = 16 << 20):
+    """``np.copyto(dst, src)`` split along the first axis over a few threads (numpy releases the GIL inside the copy).
+    One thread moves ~4 GB/s into pageable memory; a 512^3 int32 label frame is 512 MiB, so the single-threaded store
+    of a frame cost more host time than the whole frame costs on the GPU."""
+    global _COPY_POOL
+    if dst.ndim == 0 or dst.nbytes < min_bytes or dst.shape[0] < 2:
+        np.copyto(dst, src, casting="same_kind")
+        return
+    if _COPY_POOL is None:
+        _COPY_POOL = ThreadPoolExecutor(threads, thread_name_prefix="nb200-copy")
+    n = dst.shape[0]
+    cuts = np.linspace(0, n, min(threads, n) + 1).astype(int)
+    futs = [_COPY_POOL.submit(np.copyto, dst[a:b], src[a:b], "same_kind") for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    for f in futs:
+        f.result()
+
+
 def _as_tensor(x):
     if isinstance(x, torch.Tensor):
         return x
@@ -108,7 +128,7 @@ class FramePipeline:
                 with torch.cuda.device(self.dev):      # worker threads start on device 0: pin against OUR device
                     self.ev_h2d[k].synchronize()
                     buf = self._pin_in(k, src.dtype)
-                buf.copy_(src)
+                parallel_copyto(buf.numpy(), src.numpy())
                 return buf
 
             def store(t, k, dst):
@@ -121,7 +141,7 @@ class FramePipeline:
                     # (going through a converted temporary would leave a big-endian or float64 destination untouched)
                     if not isinstance(dst, np.ndarray) or not dst.flags.writeable:
                         raise TypeError("FramePipeline: the destination of a frame must be a writable ndarray / memmap slice")
-                    np.copyto(dst, self.pin_out[k].numpy(), casting="same_kind")
+                    parallel_copyto(dst, self.pin_out[k].numpy())
                 if after_store is not None:
                     after_store(t)
 

@@ -64,7 +64,7 @@ def cuda_threshold_from_samples(samples: torch.Tensor, log_domain: bool) -> Opti
     dev = samples.device
     vals = samples.to(torch.float32).contiguous()
     hist = torch.zeros(_cabi.HIST_WORDS, dtype=torch.int64, device=dev)
-    thr = torch.zeros(5, dtype=torch.float64, device=dev)
+    thr = torch.zeros(7, dtype=torch.float64, device=dev)
     vp = lambda t: C.c_void_p(t.data_ptr())                                     # noqa: E731
     with torch.cuda.device(dev):
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -78,6 +78,8 @@ def cuda_threshold_from_samples(samples: torch.Tensor, log_domain: bool) -> Opti
         return None
     if out[4] != 0.0:
         raise ValueError("attempt to get argmax of an empty sequence")           # what the reference raises
+    if log_domain:                       # labelling.py:452-455 on the scalars themselves (numpy's float32 power)
+        return float(min(10 ** np.float32(out[5]), 10 ** np.float32(out[6])))
     return float(np.float32(out[0]))
 
 

@@ -8,6 +8,9 @@ extern "C" {
 void hm_expf(const float* x, float* y, long n) {
     for (long i = 0; i < n; ++i) y[i] = nb::np_expf(x[i]);
 }
+void hm_log10f(const float* x, float* y, long n) {
+    for (long i = 0; i < n; ++i) y[i] = nb::np_log10f(x[i]);
+}
 void hm_expf_nonpos(const float* x, float* y, long n) {
     for (long i = 0; i < n; ++i) y[i] = nb::np_expf_nonpos(x[i]);
 }

@@ -89,6 +89,24 @@ def _vp(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def test_np_log10f_is_bit_exact(hostmath):
+    """numpy's float32 log10 (SVML on AVX-512 hosts, which the golden fixtures were produced on) restated in devmath.cuh:
+    identical bits on uniform, log-uniform and subnormal inputs.  On a host without AVX-512 numpy falls back to libm
+    log10f and this comparison does not apply."""
+    import ctypes as C
+    if "avx512f" not in open("/proc/cpuinfo").read().lower():
+        pytest.skip("numpy uses libm log10f on this host")
+    rng = np.random.default_rng(5)
+    xs = [rng.uniform(1e-6, 1.0, 500_000).astype(np.float32),
+          (np.float32(10.0) ** rng.uniform(-44.5, 38.0, 500_000).astype(np.float32)),
+          np.array([1.0, 0.75, 1.5, 1.4999999, 0.99999994, 1.0000001, 1e-45, 1.1754942e-38, 1.17549435e-38, 3.4e38], np.float32)]
+    for x in xs:
+        x = np.ascontiguousarray(x[np.isfinite(x) & (x > 0)])
+        y = np.empty_like(x)
+        hostmath.hm_log10f(x.ctypes.data_as(C.POINTER(C.c_float)), y.ctypes.data_as(C.POINTER(C.c_float)), C.c_long(x.size))
+        assert np.array_equal(y, np.log10(x)), int((y != np.log10(x)).sum())
+
+
 def test_np_expf_is_bit_exact(hostmath):
     rng = np.random.default_rng(0)
     x = np.concatenate([-rng.random(400_000) * 30, -rng.random(200_000) * 1e-3,
