@@ -279,6 +279,12 @@ int nb200_percentile(const float* samples, long long n, double q_percent, long l
 int nb200_finalize_opening(const float* acc, float* out, const nb200_vol* vol, const double* thr, void* stream);
 int nb200_finalize_opening_2d(const float* v, float* out, int ny, int nx, const double* thr, void* stream);
 
+/* ---- F12: Filter._remove_edges (filtering.py:969-1000, :227-250; off by default) -------------------------------
+ * In every slice of v (nz slices of ny x nx; nz = 1 for a 2-D frame) the rows of the bounding box of the positive
+ * response are found and min(margin, height) rows are zeroed at its top and bottom; the reference uses margin = 15.
+ * In place; entries <= 0 count as empty (the accumulator keeps -1 for dead voxels). */
+int nb200_remove_edges(float* v, int nz, int ny, int nx, int margin, void* stream);
+
 /* ---- F10: 2-D multi-scale LoG blobness (filtering.py:772-795, :927-930) ------------------------
  * t0/t1: the two separable second-derivative Gaussians of scipy.ndimage.gaussian_laplace (built with
  * nb200_gauss_axis and order-2 taps); acc: the sigma-loop accumulator (>= 0 alive, -1 dead).

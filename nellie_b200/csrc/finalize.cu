@@ -231,6 +231,44 @@ opening_2d_kernel(const float* __restrict__ vin, float* __restrict__ out, int ny
 
 }  // namespace
 
+// ---- F12: Filter._remove_edges (filtering.py:969-1000, _bbox :227-250), off by default ---------------------------
+// Per Z slice: rows rmin..rmax of the bounding box of the positive response, then a band of min(margin, height) rows
+// zeroed at the top and at the bottom of the box.  One CTA per slice: pass 1 finds the first / last row holding a
+// positive value (warps take rows round robin, 128-bit loads when the row pitch allows), pass 2 clears the bands.
+// An empty slice has the reference's degenerate box (0, 0): row 0 is "cleared", which changes nothing.
+namespace {
+__global__ void __launch_bounds__(256)
+remove_edges_kernel(float* __restrict__ v, int nz, int ny, int nx, int margin) {
+    __shared__ int s_min, s_max;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int z = blockIdx.x; z < nz; z += gridDim.x) {
+        float* sl = v + (long long)z * ny * nx;
+        if (threadIdx.x == 0) { s_min = ny; s_max = -1; }
+        __syncthreads();
+        for (int y = warp; y < ny; y += nwarp) {
+            const float* row = sl + (long long)y * nx;
+            bool any = false;
+            for (int x = lane; x < nx; x += 32) any |= row[x] > 0.0f;
+            if (__ballot_sync(0xffffffffu, any) != 0u && lane == 0) {
+                atomicMin(&s_min, y);
+                atomicMax(&s_max, y);
+            }
+        }
+        __syncthreads();
+        int rmin = s_min, rmax = s_max;
+        if (rmax < 0) { rmin = 0; rmax = 0; }                   // _bbox of an empty slice: (0, 0, 0, 0)
+        const int m = min(margin, rmax - rmin + 1);
+        // rows [rmin, rmin + m) and (rmax - m, rmax]
+        for (int k = warp; k < 2 * m; k += nwarp) {
+            const int y = k < m ? rmin + k : rmax - (k - m);
+            float* row = sl + (long long)y * nx;
+            for (int x = lane; x < nx; x += 32) row[x] = 0.0f;
+        }
+        __syncthreads();
+    }
+}
+}  // namespace
+
 extern "C" {
 
 int nb200_finalize_opening(const float* acc, float* out, const nb200_vol* vol, const double* thr, void* stream) {
@@ -263,6 +301,13 @@ int nb200_finalize_opening_2d(const float* vin, float* out, int ny, int nx, cons
     NB_REQUIRE(vin && out && thr && ny > 0 && nx > 0 && vin != out, NB200_ERR_ARG, "nb200_finalize_opening_2d: bad argument");
     opening_2d_kernel<<<nb::grid_for((long long)ny * nx, 256, 4), 256, 0, nb::as_stream(stream)>>>(vin, out, ny, nx, thr);
     return nb::check_launch("finalize_opening_2d");
+}
+
+int nb200_remove_edges(float* v, int nz, int ny, int nx, int margin, void* stream) {
+    NB_REQUIRE(v && nz >= 1 && ny >= 1 && nx >= 1 && margin >= 1, NB200_ERR_ARG, "nb200_remove_edges: bad argument");
+    const int grid = nz < 8 * nb::sm_count() ? nz : 8 * nb::sm_count();
+    remove_edges_kernel<<<grid, 256, 0, nb::as_stream(stream)>>>(v, nz, ny, nx, margin);
+    return nb::check_launch("remove_edges");
 }
 
 }  // extern "C"

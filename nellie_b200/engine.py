@@ -468,8 +468,8 @@ class FrangiEngine3D:
         """filtering.py:931-932: optional (off by default) zeroing of the top / bottom rows of every slice's bounding box,
         applied to the owned planes of the accumulator before _mask_volume (per-slice: no exchange between slabs)."""
         if self.p.remove_edges:
-            from .edges import remove_edge_bands_
-            remove_edge_bands_(self.acc[self.pad_lo:self.pad_lo + self.nz_own])
+            own = self.acc[self.pad_lo:self.pad_lo + self.nz_own]
+            self._call("nb200_remove_edges", _ptr(own), self.nz_own, self.ny, self.nx, 15, _stream())
 
     def finalize(self, apply_mask_volume=True, out=None):
         """filtering.py:926 (V*masks) + :1014-1018 / :952-967 (_mask_volume).  ``out``: optional device buffer of

@@ -182,8 +182,7 @@ class FrangiEngine2D:
                        int(i == 0), self.n, _ptr(self.L), st)
         self._call("nb200_log2d_combine", _ptr(self.acc), _ptr(self.L), self.n, _ptr(self.word), _ptr(self.v), st)
         if self.p.remove_edges:                 # filtering.py:931-932 (off by default)
-            from .edges import remove_edge_bands_
-            remove_edge_bands_(self.v)
+            self._call("nb200_remove_edges", _ptr(self.v), 1, self.ny, self.nx, 15, st)
         if not apply_mask_volume:
             return self.v
         return self.mask_volume(self.v)

@@ -39,7 +39,7 @@ class Filter:
                  max_radius_um: float = 1.0, alpha_sq: float = 0.5, beta_sq: float = 0.5, frob_thresh=None,
                  frob_thresh_division=2, viewer=None, device: str = "auto", low_memory: bool = False,
                  max_chunk_voxels: int = int(1e6), max_threshold_samples: int = int(1e6), sigmas=None,
-                 cuda_device=None, t_shard=None):
+                 cuda_device=None, t_shard=None, fallback=None):
         dev = (device or "auto").lower()
         if dev == "cpu":
             raise ValueError("nellie_b200.Filter implements the CUDA path only; device='cpu' belongs to "
@@ -84,7 +84,18 @@ class Filter:
         self.t_shard = None if t_shard is None else (int(t_shard[0]), int(t_shard[1]))
         self._engine = None
         self._engine_key = None
-        _cabi.load()  # fail at construction when the CUDA library is absent
+        # retry ladder of run() (adaptive.py): None = the B200 path or an exception; "reference" = continue with the
+        # reference's own CPU classes on an OOM / GPU-unavailable failure, like filtering.py:1054-1076
+        self.fallback = fallback
+        self._ctor_kwargs = dict(num_t=num_t, remove_edges=remove_edges, min_radius_um=min_radius_um,
+                                 max_radius_um=max_radius_um, alpha_sq=alpha_sq, beta_sq=beta_sq, frob_thresh=frob_thresh,
+                                 frob_thresh_division=frob_thresh_division, viewer=viewer,
+                                 max_chunk_voxels=max_chunk_voxels, max_threshold_samples=max_threshold_samples)
+        if low_memory:
+            logger.warning("nellie_b200.Filter: low_memory is accepted for compatibility and ignored (results always "
+                           "equal the reference's full-volume branch)")
+        if fallback != "reference":
+            _cabi.load()  # fail at construction when the CUDA library is absent
 
     # ---- parameters ---------------------------------------------------------------------------
     def _params(self) -> FilterParams:
@@ -229,10 +240,22 @@ class Filter:
                                    apply_mask_volume=True, on_frame=lambda k: on_frame(frames[k]),
                                    after_store=lambda k: after_store(frames[k]))
 
-    def run(self, mask=True):
-        logger.info("Running Frangi filter (nellie_b200).")
+    def _run_b200(self, mask=True):
         _require_cuda()
+        _cabi.load()
         self._get_t()
         self._allocate_memory()
         self._set_default_sigmas()
         self._run_filter(mask=mask)
+
+    def _run_reference(self, device, low_memory, mask=True):
+        """A rung of the ladder below the B200 one: the reference's own class, untouched (only with fallback='reference')."""
+        from nellie.segmentation.filtering import Filter as ReferenceFilter
+        ref = ReferenceFilter(self.im_info, device=device, low_memory=low_memory, **self._ctor_kwargs)
+        ref.run(mask=mask)
+
+    def run(self, mask=True):
+        logger.info("Running Frangi filter (nellie_b200).")
+        from .adaptive import run_with_ladder
+        run_with_ladder("Filter", lambda: self._run_b200(mask), lambda dev, low: self._run_reference(dev, low, mask),
+                        self.fallback)

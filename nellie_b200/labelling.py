@@ -135,7 +135,7 @@ class Label:
     def __init__(self, im_info, num_t=None, threshold=None, otsu_thresh_intensity=False, viewer=None,
                  chunk_z=None, flush_interval=1, min_radius_um=0.25, threshold_sampling_pixels=1_000_000,
                  histogram_nbins=256, device="auto", low_memory: bool = False, max_chunk_voxels: int = int(1e6),
-                 cuda_device=None, t_shard=None):
+                 cuda_device=None, t_shard=None, fallback=None, z_shard=None):
         dev = (device or "auto").lower()
         if dev == "cpu":
             raise ValueError("nellie_b200.Label implements the CUDA path only; device='cpu' belongs to "
@@ -171,8 +171,23 @@ class Label:
         self._cuda_device = cuda_device
         # T-sharding: (rank, world) -> frames t with t % world == rank (label ids restart per frame, labelling.py:701-706)
         self.t_shard = None if t_shard is None else (int(t_shard[0]), int(t_shard[1]))
+        # Z-sharding of every frame over the ranks of the default torch.distributed group: (rank, world);
+        # rank r labels planes z_partition(nz, world)[r] of each frame with sharded_label.label_frame_z_sharded (local
+        # CUDA CCL + seam merge) and writes its slab of the shared output file; ids equal the single-GPU numbering
+        self.z_shard = None if z_shard is None else (int(z_shard[0]), int(z_shard[1]))
+        if self.z_shard is not None and t_shard is not None:
+            raise ValueError("a Label stage is sharded over T or over Z, not both")
         self._engine = None
-        _cabi.load()
+        self.fallback = fallback       # retry ladder of run(): see adaptive.py / Filter
+        self._ctor_kwargs = dict(num_t=num_t, threshold=threshold, otsu_thresh_intensity=otsu_thresh_intensity, viewer=viewer,
+                                 chunk_z=chunk_z, flush_interval=flush_interval, min_radius_um=min_radius_um,
+                                 threshold_sampling_pixels=threshold_sampling_pixels, histogram_nbins=histogram_nbins,
+                                 max_chunk_voxels=max_chunk_voxels)
+        if low_memory or chunk_z is not None:
+            logger.warning("nellie_b200.Label: low_memory / chunk_z are accepted for compatibility and ignored (results "
+                           "always equal the reference's full-volume branch, labelling.py:538-583)")
+        if fallback != "reference":
+            _cabi.load()
 
     # ---- host scalars ---------------------------------------------------------------------------
     def _compute_min_area_pixels(self):
@@ -196,7 +211,7 @@ class Label:
         self.shape = self.frangi_memmap.shape
         from .sharding import allocate_shared_output
         self.instance_label_memmap = allocate_shared_output(self.im_info, self.im_info.pipeline_paths["im_instance_label"],
-                                                            "int32", "instance segmentation", self.t_shard)
+                                                            "int32", "instance segmentation", self.t_shard or self.z_shard)
 
     # ---- device plumbing --------------------------------------------------------------------------
     def _torch_device(self):
@@ -303,6 +318,8 @@ class Label:
         """T loop of labelling.py:697-734: every frame is uploaded once (the thresholds and the labelling share the
         device copies), labelled on the device, downloaded through a pinned buffer and written to the memmap."""
         need_raw = bool(self.otsu_thresh_intensity) or self.threshold is not None
+        if self.z_shard is not None:
+            return self._run_segmentation_z_sharded(need_raw)
         from .sharding import frames_of_rank
         frames = range(self.num_t) if self.t_shard is None else frames_of_rank(self.num_t, *self.t_shard)
         for t in frames:
@@ -328,9 +345,42 @@ class Label:
         if hasattr(self.instance_label_memmap, "flush"):
             self.instance_label_memmap.flush()
 
-    def run(self):
-        logger.info("Running semantic segmentation (nellie_b200).")
+    def _run_segmentation_z_sharded(self, need_raw):
+        """T loop with every frame split into Z slabs over the ranks (needs an initialised process group)."""
+        from .pipeline import parallel_copyto
+        from .sharded_label import label_frame_z_sharded
+        from .sharding import z_partition
+        if self.im_info.no_z:
+            raise ValueError("2-D frames are T-sharded; Z-sharding needs a Z axis")
+        rank, world = self.z_shard
+        nz = int(self.frangi_memmap.shape[1])
+        z0, z1 = z_partition(nz, world)[rank]
+        dev = self._torch_device()
+        for t in range(self.num_t):
+            if self.viewer is not None:
+                self.viewer.status = f"Extracting organelles. Frame: {t + 1} of {self.num_t}."
+            with torch.cuda.device(dev):
+                frangi = self._stage(self.frangi_memmap[t, z0:z1], "frangi")
+                raw = self._stage(self.im_memmap[t, z0:z1], "raw") if need_raw else None
+                labels = label_frame_z_sharded(frangi, z0, nz, self.min_area_pixels, self.threshold_sampling_pixels, raw,
+                                               bool(self.otsu_thresh_intensity), self.threshold)
+                host = labels.cpu()
+            parallel_copyto(self.instance_label_memmap[t, z0:z1], host.numpy())
+            if hasattr(self.instance_label_memmap, "flush"):
+                self.instance_label_memmap.flush()
+
+    def _run_b200(self):
         self._torch_device()
+        _cabi.load()
         self._get_t()
         self._allocate_memory()
         self._run_segmentation()
+
+    def _run_reference(self, device, low_memory):
+        from nellie.segmentation.labelling import Label as ReferenceLabel
+        ReferenceLabel(self.im_info, device=device, low_memory=low_memory, **self._ctor_kwargs).run()
+
+    def run(self):
+        logger.info("Running semantic segmentation (nellie_b200).")
+        from .adaptive import run_with_ladder
+        run_with_ladder("Label", self._run_b200, self._run_reference, self.fallback)

@@ -242,31 +242,57 @@ def test_library_sass_uses_tma_and_packed_f32():
         assert "DADD" in b and "DMUL" in b and "DFMA" not in b, b.split("\n")[0]
 
 
-def test_remove_edge_bands_matches_the_reference_loop():
-    """nellie_b200/edges.py against the oracle's restatement of filtering.py:969-1000, 3-D (per slice) and 2-D,
-    with empty slices, boxes lower than the margin, dead (-1) voxels and responses touching the frame border."""
-    import torch
-    from nellie_b200.edges import remove_edge_bands_
-    from oracle import pipeline as P
-    rng = np.random.default_rng(3)
-    for shape in [(6, 50, 20), (4, 17, 9), (1, 40, 8), (3, 12, 5)]:
-        v = np.zeros(shape, np.float32)
-        for z in range(shape[0]):
-            if z == 1:
-                continue                                         # an empty slice
-            r0 = int(rng.integers(0, shape[1] - 2))
-            r1 = int(rng.integers(r0, shape[1]))
-            v[z, r0:r1 + 1] = rng.random((r1 + 1 - r0, shape[2])) * (rng.random((r1 + 1 - r0, shape[2])) < 0.4)
-            v[z, r0, 0] = 1.0
-            v[z, r1, -1] = 1.0
-        spec3 = P.FrameSpec(dim_res={"X": 1.0, "Y": 1.0, "Z": 1.0, "T": 1.0}, no_z=False)
-        want = P.remove_edges(v.copy(), spec3)
-        acc = v.copy()
-        acc[(v == 0) & (rng.random(shape) < 0.5)] = -1.0        # the engines' "dead voxel" marker
-        got = remove_edge_bands_(torch.from_numpy(acc)).numpy()
-        assert np.array_equal(np.maximum(got, 0.0), want), shape
-        spec2 = P.FrameSpec(dim_res={"X": 1.0, "Y": 1.0, "T": 1.0}, no_z=True)
-        want2 = P.remove_edges(v[0].copy(), spec2)
-        got2 = remove_edge_bands_(torch.from_numpy(v[0].copy())).numpy()
-        assert np.array_equal(got2, want2), shape
-    assert not remove_edge_bands_(torch.zeros((3, 8, 8))).any()
+def test_run_ladder_matches_the_reference_rules(monkeypatch):
+    """run() of the stage classes (filtering.py:1033-1076 / adaptive_run.py:103-141): the B200 rung raises loudly by
+    default; with fallback='reference' an OOM or GPU-unavailable failure moves on to the reference's own classes
+    (cpu / high, then cpu / low), any other exception aborts at once."""
+    import sys
+    import types
+    from types import SimpleNamespace
+
+    from nellie_b200 import Filter, Label, adaptive
+
+    assert adaptive.is_oom_error(MemoryError()) and adaptive.is_oom_error(RuntimeError("CUDA out of memory. Tried ..."))
+    assert adaptive.is_gpu_unavailable_error(RuntimeError("GPU backend requested but CUDA is not available."))
+    assert not adaptive.is_oom_error(ValueError("bad shape")) and not adaptive.is_gpu_unavailable_error(ValueError("x"))
+
+    info = SimpleNamespace(no_t=True, no_z=False, shape=(1, 8, 16, 16), axes="TZYX",
+                           dim_res={"X": 0.1, "Y": 0.1, "Z": 0.1, "T": 1.0}, im_path="raw", pipeline_paths={})
+    calls = []
+
+    class FakeRef:
+        def __init__(self, im_info, device=None, low_memory=False, **kw):
+            self.args = (device, low_memory, kw)
+
+        def run(self, *a, **k):
+            calls.append(self.args[:2])
+            if not self.args[1]:
+                raise MemoryError("host out of memory")          # cpu / high-memory fails, cpu / low-memory works
+
+    for modname, cls in (("filtering", "Filter"), ("labelling", "Label")):
+        mod = types.ModuleType(f"nellie.segmentation.{modname}")
+        setattr(mod, cls, FakeRef)
+        monkeypatch.setitem(sys.modules, f"nellie.segmentation.{modname}", mod)
+    monkeypatch.setitem(sys.modules, "nellie", types.ModuleType("nellie"))
+    monkeypatch.setitem(sys.modules, "nellie.segmentation", types.ModuleType("nellie.segmentation"))
+
+    def no_gpu(*a, **k):
+        raise RuntimeError("GPU backend requested but CUDA is not available.")
+
+    for Stage in (Filter, Label):
+        calls.clear()
+        st = Stage(info, device="b200")                            # default: no ladder below the B200 rung
+        monkeypatch.setattr(st, "_run_b200", no_gpu)
+        with pytest.raises(RuntimeError, match="CUDA is not available"):
+            st.run()
+        assert calls == []
+        st = Stage(info, device="b200", fallback="reference")
+        monkeypatch.setattr(st, "_run_b200", no_gpu)
+        st.run()
+        assert calls == [("cpu", False), ("cpu", True)]
+        calls.clear()
+        st = Stage(info, device="b200", fallback="reference")
+        monkeypatch.setattr(st, "_run_b200", lambda *a, **k: (_ for _ in ()).throw(ValueError("not a memory problem")))
+        with pytest.raises(ValueError):
+            st.run()
+        assert calls == []

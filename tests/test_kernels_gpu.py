@@ -178,3 +178,65 @@ def test_opening_matches_scipy(shape, density):
         got = out2.cpu().numpy()
         assert np.array_equal(got[3:shape[0] - 2], ref[3:shape[0] - 2])
         assert (got[:3] == 7.0).all() and (got[shape[0] - 2:] == 7.0).all()
+
+
+def test_remove_edges_kernel_matches_the_reference_loop():
+    """nb200_remove_edges against the oracle's restatement of filtering.py:969-1000, 3-D (per slice) and 2-D,
+    with empty slices, boxes lower than the margin, dead (-1) voxels and responses touching the frame border."""
+    import torch
+    from nellie_b200 import _cabi
+
+    def remove_edge_bands_(t):
+        d = t.cuda().contiguous()
+        shp = d.shape if d.dim() == 3 else (1,) + tuple(d.shape)
+        _cabi.call("nb200_remove_edges", C.c_void_p(d.data_ptr()), int(shp[0]), int(shp[1]), int(shp[2]), 15,
+                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return d.cpu()
+
+    from oracle import pipeline as P
+    rng = np.random.default_rng(3)
+    for shape in [(6, 50, 20), (4, 17, 9), (1, 40, 8), (3, 12, 5)]:
+        v = np.zeros(shape, np.float32)
+        for z in range(shape[0]):
+            if z == 1:
+                continue                                         # an empty slice
+            r0 = int(rng.integers(0, shape[1] - 2))
+            r1 = int(rng.integers(r0, shape[1]))
+            v[z, r0:r1 + 1] = rng.random((r1 + 1 - r0, shape[2])) * (rng.random((r1 + 1 - r0, shape[2])) < 0.4)
+            v[z, r0, 0] = 1.0
+            v[z, r1, -1] = 1.0
+        spec3 = P.FrameSpec(dim_res={"X": 1.0, "Y": 1.0, "Z": 1.0, "T": 1.0}, no_z=False)
+        want = P.remove_edges(v.copy(), spec3)
+        acc = v.copy()
+        acc[(v == 0) & (rng.random(shape) < 0.5)] = -1.0        # the engines' "dead voxel" marker
+        got = remove_edge_bands_(torch.from_numpy(acc)).numpy()
+        assert np.array_equal(np.maximum(got, 0.0), want), shape
+        spec2 = P.FrameSpec(dim_res={"X": 1.0, "Y": 1.0, "T": 1.0}, no_z=True)
+        want2 = P.remove_edges(v[0].copy(), spec2)
+        got2 = remove_edge_bands_(torch.from_numpy(v[0].copy())).numpy()
+        assert np.array_equal(got2, want2), shape
+    assert not remove_edge_bands_(torch.zeros((3, 8, 8))).any()
+
+
+def test_filter_with_remove_edges_matches_the_oracle():
+    """Filter(remove_edges=True) (filtering.py:931-932) end to end, 3-D and 2-D, against the oracle."""
+    from types import SimpleNamespace
+    from nellie_b200 import Filter
+    from nellie_b200.phantoms import tubular_phantom_np
+    from oracle import pipeline as P
+    for shape, no_z in [((20, 64, 72), False), ((96, 104), True)]:
+        dim_res = {"X": 0.1, "Y": 0.1, "Z": None if no_z else 0.1, "T": 1.0}
+        raw = tubular_phantom_np(shape if not no_z else (1,) + shape, seed=41, n_tubes=5)
+        raw = raw if not no_z else raw[0]
+        info = SimpleNamespace(no_t=True, no_z=no_z, shape=(1,) + raw.shape, axes="TYX" if no_z else "TZYX", dim_res=dim_res)
+        f = Filter(info, device="b200", remove_edges=True)
+        f._get_t()
+        f._set_default_sigmas()
+        got = f.filter_frame_host(raw)
+        ref = P.filter_frame(raw, P.FrameSpec(dim_res=dim_res, no_z=no_z, remove_edges=True))
+        assert np.array_equal(got > 0, ref > 0), shape
+        if no_z:
+            assert (np.abs(got - ref) <= 1e-5 * np.abs(ref) + 1e-6 * np.abs(ref).max()).all()
+        else:
+            assert np.array_equal(got, ref), shape
+

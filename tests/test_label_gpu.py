@@ -166,3 +166,19 @@ def test_sharded_labeller_on_one_gpu_equals_the_reference_labels(tmp_path):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_z_sharded_label_on_two_gpus():
+    """Needs >= 2 GPUs (skipped on a single-GPU box): torchrun scripts/zshard_label_check.py — the Z-sharded labeller
+    against the single-GPU kernel on a slab pair, and Label(z_shard=(rank, world)).run() on files against Label.run()."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29543",
+                        os.path.join(root, "scripts", "zshard_label_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
