@@ -202,6 +202,8 @@ class FrangiEngine3D:
                           and self.nz_buf * ny * nx < 2 ** 32 and ny >= 5 and nx >= 12)
         self.fast_ws = torch.zeros(int(self.lib.nb200_hessian_fast_workspace_bytes()) // 4, dtype=torch.int32, device=dev)
         self.max_scale = float(1.0 / (np.float64(self.fd[1::2].min()) ** 2))
+        self.use_graph = False   # replay the per-frame sequence as a CUDA graph (see filter_frame); ZShardedFilter turns it on
+        self._graphs, self._eager_done = {}, {}
         self.diag = None      # set to a zeroed int64[8] device tensor to collect candidate / survivor counts (tests)
         self.fuse_yx = True   # Y and X blur passes in one kernel (nb200_gauss_yx); False = one kernel per axis
         self.launches = 0     # C-ABI calls
@@ -495,10 +497,47 @@ class FrangiEngine3D:
         return dst
 
     def filter_frame(self, frame: torch.Tensor, apply_mask_volume=True, out=None) -> torch.Tensor:
-        """Device tensor in, device tensor out (the engine's own output buffer unless ``out`` is given)."""
+        """Device tensor in, device tensor out (the engine's own output buffer unless ``out`` is given).
+
+        With ``use_graph`` the kernel + collective sequence of a frame (~250 launches, plus the NCCL all-gathers and
+        halo exchanges of a Z-sharded run) is captured as one CUDA graph on the second call and replayed afterwards:
+        on 8 GPUs a slab's kernels take 11 ms while issuing them from Python took 16 ms.  All buffers are engine-owned
+        and static; only the upload of the frame stays outside the graph.  Profiling (``self.profile``) and a
+        caller-provided ``out`` buffer other than the captured one fall back to eager launches."""
         self.load_frame(frame)
-        self.run_sigmas()
-        return self.finalize(apply_mask_volume, out=out)
+        key = (bool(apply_mask_volume), bool(self.p.mask), self.fast_path, None if out is None else out.data_ptr())
+        if not self.use_graph or self.profile is not None:
+            self.run_sigmas()
+            return self.finalize(apply_mask_volume, out=out)
+        if key in self._graphs:
+            graph, res, launches, kernels = self._graphs[key]
+            self.cur = 0
+            graph.replay()
+            self.launches += launches
+            self.kernels += kernels
+            return res
+        if not self._eager_done.get(key):
+            self._eager_done[key] = True                    # first call: plain launches (lazy allocations, warm caches)
+            self.run_sigmas()
+            return self.finalize(apply_mask_volume, out=out)
+        l0, k0 = self.launches, self.kernels
+        try:
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                self.cur = 0
+                self.run_sigmas()
+                res = self.finalize(apply_mask_volume, out=out)
+        except Exception:                                   # capture is an optimisation: eager launches from now on
+            self.use_graph = False
+            torch.cuda.synchronize(self.device)
+            self.load_frame(frame)
+            self.run_sigmas()
+            return self.finalize(apply_mask_volume, out=out)
+        self._graphs[key] = (graph, res, self.launches - l0, self.kernels - k0)
+        self.cur = 0
+        graph.replay()                                      # capture does not execute: run the frame now
+        return res
 
     def mask_volume(self, v: torch.Tensor) -> torch.Tensor:
         """_mask_volume (filtering.py:952-967) of an already computed response ``v`` (>= 0)."""

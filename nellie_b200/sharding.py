@@ -186,6 +186,10 @@ class ZShardedFilter:
         e.reduce_hist_bins = self.comm.reduce_hist_bins
         e.reduce_hstats = self.comm.reduce_hstats
         e.fold_state = self.comm.fold_state
+        # a slab's kernels are short: issuing ~250 launches + collectives per frame from Python costs more than they run
+        # for on 8 GPUs; capture them once and replay (NB200_NO_GRAPH=1 keeps eager launches)
+        import os
+        e.use_graph = self.world > 1 and not os.environ.get("NB200_NO_GRAPH")
         e.gather_samples = self._gather_samples
         self._pinned = None
 
