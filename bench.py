@@ -391,8 +391,12 @@ def run_b200_arm(args):
                                  "bound_voxels_per_s": float(min(lt[0].item(), lt[1].item())) * 1e9 / 4.0,
                                  "how": "1 GiB pinned copies per direction, all ranks at once, after the timed region"}
 
+    # captured CUDA graphs hold NCCL work: release them before the communicator goes away (otherwise the teardown hangs)
+    eng._graphs.clear()
+    torch.cuda.synchronize(dev)
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
     peaks, which = measured_peaks()
@@ -452,6 +456,7 @@ def run_b200_arm(args):
             "kernel_ms_per_step": breakdown, "kernel_ms_per_sigma": per_sigma}
     emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
