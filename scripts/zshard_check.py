@@ -17,12 +17,18 @@ for shape, dim_res, sigmas in [((64, 96, 160), {"X": 0.1, "Y": 0.1, "Z": 0.1, "T
     params = FilterParams(dim_res=dim_res, no_z=False, sigmas=sigmas)
     full = tubular_phantom(shape, seed=9, device=dev, n_tubes=12)
     zs = ZShardedFilter(shape, params, dev)
-    out = zs.filter_frame(zs.slab_of(full)).clone()
+    slab = zs.slab_of(full)
+    out = zs.filter_frame(slab).clone()                      # eager launches
+    out2 = zs.filter_frame(slab).clone()                     # captured as a CUDA graph (kernels + NCCL), then replayed
+    out3 = zs.filter_frame(slab).clone()                     # replay
+    assert zs.engine.use_graph and len(zs.engine._graphs) == 1, "graph capture did not happen"
+    graph_ok = torch.equal(out, out2) and torch.equal(out, out3)
     sp = zs.engine.sigma_records()
+    zs.engine._graphs.clear()
     ref_eng = FrangiEngine3D(shape, params, device=dev)
     ref = ref_eng.filter_frame(full)
     sp_ref = ref_eng.sigma_records()
-    same = torch.equal(out, ref[zs.z0:zs.z1])
+    same = torch.equal(out, ref[zs.z0:zs.z1]) and graph_ok
     same_sp = bool((sp[:, :6] == sp_ref[:, :6]).all())
     print(f"rank {rank}/{world} shape {shape}: slab [{zs.z0},{zs.z1}) identical={same} scalars identical={same_sp} "
           f"nonzero={int((out > 0).sum())}", flush=True)
