@@ -631,6 +631,7 @@ struct FrangiFastParams {
     float alpha_sq, beta_sq;
     const double* spd;
     unsigned long long* diag;
+    int debug;               // profiling experiments only (NB200_K3_DEBUG): 1 = no eigen-solves, 2 = no exact evaluation at all
 };
 
 template <int MODE, int K>
@@ -687,7 +688,7 @@ struct FrangiFastEpi {
     __device__ __forceinline__ void solve(int cnt) {
         __syncwarp();
         const int e = rq_n - cnt + lane;
-        if (lane < cnt) {
+        if (lane < cnt && p.debug == 0) {
             const unsigned at = __float_as_uint(wq.rq[6][e]);
             const float vv = eig_vesselness(wq.rq[0][e], wq.rq[1][e], wq.rq[2][e], wq.rq[3][e], wq.rq[4][e], wq.rq[5][e],
                                             p.alpha_sq, p.beta_sq, gamma_sq);
@@ -822,6 +823,7 @@ struct FrangiFastEpi {
         }
         // ---- push the candidates: one ballot per voxel slot, every lane stays active (the per-lane loop over set bits
         //      of the first version ran with 14 of 32 threads and cost 12 % of the kernel's instructions) ----
+        if (p.debug == 2) cand = 0u;
         if (__ballot_sync(0xffffffffu, cand != 0u) != 0u) {
             const unsigned lt = (1u << lane) - 1u;
             int tail = cq_head + cq_n;
@@ -1084,6 +1086,10 @@ int nb200_frangi_fast(const float* gauss, float* acc, const nb200_vol* vol, cons
         p.beta_sq = beta_sq;
         p.spd = sp;
         p.diag = diag;
+        {
+            static const int dbg = getenv("NB200_K3_DEBUG") ? atoi(getenv("NB200_K3_DEBUG")) : 0;
+            p.debug = dbg;
+        }
         rc = div_mode == hm::DIV_POW2 ? hf::launch_frangi<2>(map, v, k, m, p, st) : hf::launch_frangi<1>(map, v, k, m, p, st);
         if (rc) return rc;
     }
