@@ -968,6 +968,13 @@ int fast_supported(const float* g, const nb200_vol& v, int div_mode, const char*
     return NB200_OK;
 }
 
+// NB200_FAST_CTAS=1 pads the dynamic shared memory of the march kernels beyond half an SM so that one CTA is resident
+// per SM (experiment: leave room for the FP64-bound blur of the next sigma on a second stream)
+size_t padded_smem(size_t bytes) {
+    static const int one = getenv("NB200_FAST_CTAS") ? atoi(getenv("NB200_FAST_CTAS")) : 2;
+    return (one == 1 && bytes < 118 * 1024) ? (size_t)118 * 1024 : bytes;
+}
+
 template <class Kern>
 int set_smem(Kern kernel, size_t bytes, bool& done) {
     if (done) return NB200_OK;
@@ -987,9 +994,10 @@ int launch_stats(const CUtensorMap& map, const float* g, const nb200_vol& v, con
                  const StatsFastParams& p, cudaStream_t st) {
     static bool done = false;
     auto kernel = stats_fast_kernel<MODE, D_STATS>;
-    int rc = set_smem(kernel, sizeof(Ring<D_STATS>), done);
+    const size_t smem = padded_smem(sizeof(Ring<D_STATS>));
+    int rc = set_smem(kernel, smem, done);
     if (rc) return rc;
-    kernel<<<(unsigned)m.n_ctas, NT, sizeof(Ring<D_STATS>), st>>>(map, v, k, m.zi0, m.zi1, m.zchunk, p);
+    kernel<<<(unsigned)m.n_ctas, NT, smem, st>>>(map, v, k, m.zi0, m.zi1, m.zchunk, p);
     rc = nb::check_launch("hessian_stats_fast");
     if (rc) return rc;
     stats_fixup_kernel<MODE><<<2 * nb::sm_count(), 256, 0, st>>>(g, v, k, p.wl, p.hstats, m.zi0);
@@ -1002,9 +1010,10 @@ int launch_frangi_cfg(const CUtensorMap& map, const nb200_vol& v, const Consts& 
                       const FrangiFastParams& p, cudaStream_t st) {
     static bool done = false;
     auto kernel = frangi_fast_kernel<MODE, D, K, L, MINB>;
-    int rc = set_smem(kernel, sizeof(FrangiSmem<D>), done);
+    const size_t smem = padded_smem(sizeof(FrangiSmem<D>));
+    int rc = set_smem(kernel, smem, done);
     if (rc) return rc;
-    kernel<<<(unsigned)m.n_ctas, NT, sizeof(FrangiSmem<D>), st>>>(map, v, k, m.zi0, m.zi1, m.zchunk, p);
+    kernel<<<(unsigned)m.n_ctas, NT, smem, st>>>(map, v, k, m.zi0, m.zi1, m.zchunk, p);
     return nb::check_launch("frangi_fast");
 }
 template <int MODE>
