@@ -310,6 +310,19 @@ int nb200_label_frame(const float* frangi, const float* raw, int use_intensity, 
 int nb200_ccl_label(const unsigned char* mask, int nz, int ny, int nx, int connectivity_full, int* labels,
                     void* workspace, long long* n_labels, void* stream);
 
+/* ---- Network stage, the array kernels its GPU backend runs ------------------------------------------------
+ * skel / labels: int32 frames (nz = 1 for 2-D).  Everything else of the stage (skeletonize, _add_missing_skeleton_labels,
+ * _relabel_objects) runs on the host in the reference too and is not part of this library.
+ * nb200_pixel_class: networking.py:669-680 — out (uint8) = skel > 0 ? min(4, set voxels in the 3^d window, zero outside) : 0.
+ * nb200_branch_labels: networking.py:758-797 — scipy.ndimage.label(ones(3^d)) of (pixel_class > 0) & (pixel_class != 4);
+ *   workspace = nb200_label_workspace_bytes(), ids in raster order of each component's first voxel.
+ * nb200_remove_connected_label_pixels: networking.py:261-296 — a labelled voxel off the frame boundary whose 3^d window
+ *   holds two different positive labels becomes 0 (out != labels). */
+int nb200_pixel_class(const int* skel, int nz, int ny, int nx, unsigned char* out, void* stream);
+int nb200_branch_labels(const unsigned char* pixel_class, int nz, int ny, int nx, int* labels, void* workspace,
+                        long long* n_labels, void* stream);
+int nb200_remove_connected_label_pixels(const int* labels, int nz, int ny, int nx, int* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,6 +77,9 @@ _SIGS = {
                                  C.c_int),
     "nb200_finalize_frob_fast": ([_p, _p, C.c_double, C.c_double, C.c_double, C.c_int, _p, _p], C.c_int),
     "nb200_finalize_frob_resolve": ([_p, _p, _p], C.c_int),
+    "nb200_pixel_class": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
+    "nb200_branch_labels": ([_p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p], C.c_int),
+    "nb200_remove_connected_label_pixels": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_remove_edges": ([_p, C.c_int, C.c_int, C.c_int, C.c_int, _p], C.c_int),
     "nb200_fold_records": ([_p, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_frangi_fast": ([_p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, _p, _p, _p], C.c_int),

@@ -501,3 +501,114 @@ int nb200_ccl_label(const unsigned char* mask, int nz, int ny, int nx, int conne
 }
 
 }  // extern "C"
+
+// ==================================================================================================================
+// Network stage, the three array kernels the reference runs on its GPU backend:
+//   nellie/segmentation/networking.py:669-680  _get_pixel_class_impl            3^d neighbour count of the skeleton
+//   nellie/segmentation/networking.py:758-797  _get_branch_skel_labels          label() of the non-junction skeleton
+//   nellie/segmentation/networking.py:261-296  _remove_connected_label_pixels   3^d min / max label filters
+// (skeletonize, _add_missing_skeleton_labels and _relabel_objects stay on the host in the reference as well.)
+// ==================================================================================================================
+namespace {
+
+// out = skel > 0 ? min(4, number of set voxels in the 3^d window, zero outside the frame) : 0      (uint8)
+__global__ void __launch_bounds__(THREADS)
+pixel_class_kernel(const int* __restrict__ skel, Dims d, unsigned char* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
+         i += (long long)gridDim.x * blockDim.x) {
+        unsigned char res = 0;
+        if (__ldg(skel + i) > 0) {
+            const int z = (int)(i / d.plane);
+            const long long rem = i - (long long)z * d.plane;
+            const int y = (int)(rem / d.nx), x = (int)(rem - (long long)y * d.nx);
+            int cnt = 0;
+            for (int dz = (d.nz > 1 ? -1 : 0); dz <= (d.nz > 1 ? 1 : 0); ++dz) {
+                const int zz = z + dz;
+                if (zz < 0 || zz >= d.nz) continue;
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int yy = y + dy;
+                    if (yy < 0 || yy >= d.ny) continue;
+                    const int* row = skel + (long long)zz * d.plane + (long long)yy * d.nx;
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int xx = x + dx;
+                        if (xx >= 0 && xx < d.nx) cnt += __ldg(row + xx) > 0 ? 1 : 0;
+                    }
+                }
+            }
+            res = (unsigned char)(cnt > 4 ? 4 : cnt);
+        }
+        out[i] = res;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS)
+non_junction_mask_kernel(const unsigned char* __restrict__ pixel_class, long long n, unsigned char* __restrict__ mask) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned char c = pixel_class[i];
+        mask[i] = (c > 0 && c != 4) ? 1 : 0;
+    }
+}
+
+// out = label, except for labelled voxels off the frame boundary whose 3^d window holds two different positive labels
+__global__ void __launch_bounds__(THREADS)
+remove_connected_kernel(const int* __restrict__ labels, Dims d, int* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int me = __ldg(labels + i);
+        int res = me;
+        if (me > 0) {
+            const int z = (int)(i / d.plane);
+            const long long rem = i - (long long)z * d.plane;
+            const int y = (int)(rem / d.nx), x = (int)(rem - (long long)y * d.nx);
+            const bool boundary = y == 0 || y == d.ny - 1 || x == 0 || x == d.nx - 1 || (d.nz > 1 && (z == 0 || z == d.nz - 1));
+            if (!boundary) {
+                int lo = me, hi = me;
+                for (int dz = (d.nz > 1 ? -1 : 0); dz <= (d.nz > 1 ? 1 : 0); ++dz)
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int* row = labels + i + (long long)dz * d.plane + (long long)dy * d.nx;
+#pragma unroll
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int v = __ldg(row + dx);
+                            if (v > 0) { lo = min(lo, v); hi = max(hi, v); }
+                        }
+                    }
+                if (lo != hi) res = 0;
+            }
+        }
+        out[i] = res;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int nb200_pixel_class(const int* skel, int nz, int ny, int nx, unsigned char* out, void* stream) {
+    NB_REQUIRE(skel && out && nz >= 1 && ny >= 1 && nx >= 1, NB200_ERR_ARG, "nb200_pixel_class: bad argument");
+    const Dims d = make_dims(nz, ny, nx);
+    pixel_class_kernel<<<gs(d.total), THREADS, 0, nb::as_stream(stream)>>>(skel, d, out);
+    return nb::check_launch("pixel_class");
+}
+
+int nb200_branch_labels(const unsigned char* pixel_class, int nz, int ny, int nx, int* labels, void* workspace,
+                        long long* n_labels, void* stream) {
+    NB_REQUIRE(pixel_class && labels && workspace && n_labels, NB200_ERR_ARG, "nb200_branch_labels: null argument");
+    const long long n = (long long)nz * ny * nx;
+    NB_REQUIRE(n < 2147483000LL, NB200_ERR_UNSUPPORTED, "nb200_branch_labels: frame exceeds int32 voxel indexing");
+    auto al = [](long long b) { return (b + 255) / 256 * 256; };
+    unsigned char* mask = reinterpret_cast<unsigned char*>(static_cast<char*>(workspace) + al(4 * n));   // mask_a of the label workspace
+    non_junction_mask_kernel<<<gs(n), THREADS, 0, nb::as_stream(stream)>>>(pixel_class, n, mask);
+    int rc = nb::check_launch("branch_labels(mask)");
+    if (rc) return rc;
+    return nb200_ccl_label(mask, nz, ny, nx, 1, labels, workspace, n_labels, stream);
+}
+
+int nb200_remove_connected_label_pixels(const int* labels, int nz, int ny, int nx, int* out, void* stream) {
+    NB_REQUIRE(labels && out && labels != out && nz >= 1 && ny >= 1 && nx >= 1, NB200_ERR_ARG,
+               "nb200_remove_connected_label_pixels: bad argument");
+    const Dims d = make_dims(nz, ny, nx);
+    remove_connected_kernel<<<gs(d.total), THREADS, 0, nb::as_stream(stream)>>>(labels, d, out);
+    return nb::check_launch("remove_connected_label_pixels");
+}
+
+}  // extern "C"

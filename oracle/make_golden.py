@@ -126,6 +126,34 @@ def label_only_cases():
         print(f"{name}: shape={fr.shape} labels={int(labels.max())} min_area={lab.min_area_pixels}")
 
 
+def network_cases():
+    """The Network stage's array kernels (networking.py:261-296, :669-680, :758-797) executed on synthetic skeletons:
+    random 26-connected walks labelled by object, with crossings (junctions), touching objects and border voxels."""
+    from types import SimpleNamespace
+    import scipy.ndimage as ndi
+    ref_shim.load()
+    from nellie.segmentation.networking import Network
+    rng = np.random.default_rng(17)
+    for name, shape, no_z in (("network3d", (24, 40, 48), False), ("network2d", (64, 72), True)):
+        skel = np.zeros(shape, np.int32)
+        nd = len(shape)
+        for obj in range(1, 13):
+            p = np.array([rng.integers(0, s) for s in shape])
+            for _ in range(int(rng.integers(20, 90))):
+                skel[tuple(p)] = obj
+                p = np.clip(p + rng.integers(-1, 2, nd), 0, np.array(shape) - 1)
+        me = SimpleNamespace(im_info=SimpleNamespace(no_z=no_z), low_memory=False, xp=np, ndi=ndi)
+        cleaned = Network._remove_connected_label_pixels_impl(me, skel, np, ndi)
+        pixel_class = Network._get_pixel_class_impl(me, skel, np, ndi)
+        branch = Network._get_branch_skel_labels(me, pixel_class, force_cpu=True)
+        path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+        np.savez_compressed(path, skel=skel, cleaned=np.asarray(cleaned).astype(np.int32),
+                            pixel_class=np.asarray(pixel_class).astype(np.uint8), branch=np.asarray(branch).astype(np.int32),
+                            meta=np.asarray(json.dumps(dict(no_z=no_z))))
+        print(f"{name}: shape={shape} skeleton voxels={int((skel > 0).sum())} removed={int(((cleaned == 0) & (skel > 0)).sum())} "
+              f"junctions={int((pixel_class == 4).sum())} branches={int(branch.max())}")
+
+
 def main():
     from nellie_b200.phantoms import tubular_phantom_np
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -159,6 +187,7 @@ def main():
     # (8) Filter._run_frame(t, mask=False) (filtering.py:910-933): no Frobenius gate
     save_case("phantom3d_nomask", tubular_phantom_np((20, 40, 48), seed=27, n_tubes=4), iso, False, run_mask=False)
     label_only_cases()
+    network_cases()
 
 
 if __name__ == "__main__":

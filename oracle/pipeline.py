@@ -533,3 +533,36 @@ def segment_frame(raw, spec: FrameSpec):
     fr = filter_frame(raw, spec)
     it, ft = label_thresholds(raw, fr, spec)
     return fr, label_frame(fr, spec, ft, raw=raw, intensity_thresh=it)
+
+
+# ---------------------------------------------------------------------------------------------
+# Network stage, array kernels of its GPU backend — restated for the parity tests
+# ---------------------------------------------------------------------------------------------
+def network_pixel_class(skel, no_z: bool):
+    """networking.py:669-680 (_get_pixel_class_impl)."""
+    m = (np.asarray(skel) > 0).astype(np.uint8)
+    w = np.ones((3, 3) if no_z else (3, 3, 3))
+    s = ndi.convolve(m, weights=w, mode="constant", cval=0) * m
+    s[s > 4] = 4
+    return s
+
+
+def network_branch_labels(pixel_class, no_z: bool):
+    """networking.py:758-797 (_get_branch_skel_labels)."""
+    pc = np.asarray(pixel_class)
+    lab, _ = ndi.label((pc > 0) & (pc != 4), structure=np.ones((3, 3) if no_z else (3, 3, 3)))
+    return lab
+
+
+def network_remove_connected(labels, no_z: bool):
+    """networking.py:261-296 (_remove_connected_label_pixels_impl)."""
+    labels = np.asarray(labels)
+    size = (3, 3) if no_z else (3, 3, 3)
+    mx = ndi.maximum_filter(labels, size=size, mode="constant", cval=0)
+    bg = int(labels.max()) + 1
+    mn = ndi.minimum_filter(np.where(labels == 0, bg, labels), size=size, mode="constant", cval=bg)
+    mn = np.where(mn == bg, 0, mn)
+    amb = (labels > 0) & (mn > 0) & (mx > 0) & (mn != mx)
+    inner = np.zeros(labels.shape, bool)
+    inner[tuple(slice(1, -1) for _ in labels.shape)] = True
+    return np.where(amb & inner, 0, labels)

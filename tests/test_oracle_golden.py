@@ -80,3 +80,15 @@ def test_filter_does_not_mutate_float32_input():
     keep = raw.copy()
     P.frangi_frame(raw, spec)
     assert np.array_equal(raw, keep)
+
+
+@pytest.mark.parametrize("name", ["network3d", "network2d"])
+def test_network_kernels_match_reference(name):
+    """Array kernels of the Network stage (networking.py:261-296, :669-680, :758-797) against the executed reference."""
+    import json
+    z = np.load(f"{__import__('conftest').GOLDEN_DIR}/{name}.npz")
+    no_z = json.loads(str(z["meta"]))["no_z"]
+    assert np.array_equal(P.network_remove_connected(z["skel"], no_z), z["cleaned"])
+    pc = P.network_pixel_class(z["skel"], no_z)
+    assert np.array_equal(pc, z["pixel_class"])
+    assert np.array_equal(P.network_branch_labels(pc, no_z), z["branch"])
