@@ -79,6 +79,10 @@ class NetworkKernels:
         labels are set to 0."""
         nz, ny, nx = self._dims(skel_labels.shape)
         d, was_np = self._dev_i32(skel_labels)
+        if not self.im_info.no_z and nz == 1:
+            # a one-plane 3-D stack: every voxel lies on the Z boundary, which the reference never modifies
+            # (networking.py:285-291); the C entry point reads nz == 1 as a 2-D frame, so this case stays here
+            return d.cpu().numpy() if was_np else d.clone()
         out = torch.empty_like(d)
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.nb200_remove_connected_label_pixels(_ptr(d), nz, ny, nx, _ptr(out), self._stream()),
