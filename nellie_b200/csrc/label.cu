@@ -17,8 +17,6 @@
 // algorithmic; the parent array and the byte masks are honest extra traffic).
 #include "common.cuh"
 
-#include <stdlib.h>
-
 namespace {
 
 constexpr int OUTSIDE = -2;
@@ -70,183 +68,96 @@ __device__ __forceinline__ void unite(int* parent, int a, int b) {
     }
 }
 
-__device__ __forceinline__ void link_outside(int* parent, int a) {
-    while (true) {
-        a = find_root(parent, a);
-        if (a < 0) return;
-        const int old = atomicMin(parent + a, OUTSIDE);
-        if (old == a) return;
-        a = old;
-    }
+// ---- membership words ------------------------------------------------------------------------------
+// Every mask of this file is packed: one 32-bit word per 32-voxel strip of a row, word [row][xw], bit k = voxel
+// x = 32 xw + k, bits beyond nx are 0 (row = z * ny + y, wpr = ceil(nx / 32) words per row).  All indices fit int32
+// (the entry points refuse frames of 2^31 voxels or more).
+__device__ __forceinline__ unsigned valid_bits(const Dims& d, int xw) {
+    const int nvalid = d.nx - xw * 32;
+    return nvalid >= 32 ? 0xffffffffu : ((1u << nvalid) - 1u);
 }
 
-// ---- threshold ---------------------------------------------------------------------------------
+// members of the set `want` (1: the mask, 0: its complement inside the frame) in word (row, xw)
+__device__ __forceinline__ unsigned set_word(const unsigned* __restrict__ bits, const Dims& d, int wpr, int row, int xw,
+                                             unsigned char want) {
+    const unsigned w = __ldg(bits + (long long)row * wpr + xw);
+    return want ? w : (~w & valid_bits(d, xw));
+}
+
+// mask = (frangi * (raw > intensity_thr)) > frangi_thr, one warp per strip
 __global__ void __launch_bounds__(THREADS)
-threshold_mask_kernel(const float* __restrict__ frangi, const float* __restrict__ raw, int use_intensity,
-                      float intensity_thresh, const double* __restrict__ thr, long long n,
-                      unsigned char* __restrict__ mask) {
+threshold_bits_kernel(const float* __restrict__ frangi, const float* __restrict__ raw, int use_intensity,
+                      float intensity_thresh, const double* __restrict__ thr, Dims d, unsigned* __restrict__ bits) {
     const bool none = thr[3] != 0.0;            // no samples: mask = zeros (labelling.py:475-476)
     const float cut = (float)thr[0];
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x) {
-        float f = __ldg(frangi + i);
-        if (use_intensity) f = f * ((__ldg(raw + i) > intensity_thresh) ? 1.0f : 0.0f);   // labelling.py:550-552
-        mask[i] = (!none && f > cut) ? 1 : 0;
+    const int wpr = (d.nx + 31) / 32;
+    const int nwin = d.nz * d.ny * wpr;
+    const int lane = threadIdx.x & 31;
+    constexpr int U = 4;                                    // strips per warp and iteration: four loads in flight
+    const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+    for (int w0 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * U; w0 < nwin; w0 += nwarps * U) {
+        float f[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int w = w0 + k;
+            const int row = w / wpr;
+            const int x = (w - row * wpr) * 32 + lane;
+            f[k] = -INFINITY;
+            if (w < nwin && x < d.nx) {
+                const long long i = (long long)row * d.nx + x;
+                f[k] = __ldg(frangi + i);
+                if (use_intensity) f[k] = f[k] * ((__ldg(raw + i) > intensity_thresh) ? 1.0f : 0.0f);   // labelling.py:550-552
+            } else if (w < nwin) {
+                f[k] = -INFINITY;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int w = w0 + k;
+            const int row = w / wpr;
+            const bool inside = w < nwin && (w - row * wpr) * 32 + lane < d.nx;
+            const unsigned b = __ballot_sync(0xffffffffu, inside && !none && f[k] > cut);
+            if (lane == 0 && w < nwin) bits[w] = b;
+        }
     }
 }
 
-// ---- CCL ---------------------------------------------------------------------------------------
-// `want` selects the set: voxels with mask == want are in the set.
+// bytes -> words (entry points that take a uint8 mask); TEST: 0 -> byte != 0, 1 -> byte in 1..3 (a skeleton voxel that
+// is not a junction, networking.py:758-797)
+template <int TEST>
 __global__ void __launch_bounds__(THREADS)
-ccl_init_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims d, int* __restrict__ parent) {
-    // one warp per 32-wide x window; windows per row = ceil(nx/32)
+pack_bits_kernel(const unsigned char* __restrict__ mask, Dims d, unsigned* __restrict__ bits) {
     const int wpr = (d.nx + 31) / 32;
-    const long long nwin = (long long)d.nz * d.ny * wpr;
+    const int nwin = d.nz * d.ny * wpr;
     const int lane = threadIdx.x & 31;
-    for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < nwin;
-         w += ((long long)gridDim.x * blockDim.x) >> 5) {
-        const long long row = w / wpr;
-        const int x = (int)(w - row * wpr) * 32 + lane;
-        const long long idx = row * d.nx + x;
-        const bool in = x < d.nx && mask[idx] == want;
-        const unsigned bits = __ballot_sync(0xffffffffu, in);
+    for (int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5); w < nwin;
+         w += (int)(((long long)gridDim.x * blockDim.x) >> 5)) {
+        const int row = w / wpr;
+        const int x = (w - row * wpr) * 32 + lane;
+        bool in = false;
         if (x < d.nx) {
-            int val = NOT_IN_SET;
-            if (in) {
-                const unsigned below_zero = ~bits & ((1u << lane) - 1u);
-                const int start = below_zero ? 32 - __clz(below_zero) : 0;
-                val = (int)(idx - lane + start);
-            }
-            parent[idx] = val;
+            const unsigned char c = mask[(long long)row * d.nx + x];
+            in = TEST == 0 ? c != 0 : (c > 0 && c != 4);
         }
+        const unsigned b = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) bits[w] = b;
     }
 }
 
-// Unions are found in lock step (every lane tests the same neighbour relation of its own voxel) but carried out
-// through a per-warp shared-memory queue of (a, b) pairs: 32 pairs are united at a time, one per lane, so the
-// pointer-chasing find / atomicMin loops run with full warps instead of the one or two lanes per instruction
-// that a voxel-by-voxel unite() leaves active (measured: 1.2-1.7 active threads per instruction, 9-16 ms per merge
-// of a 512^3 frame).
-template <bool FULL_CONN, bool BORDER_OUTSIDE>
-__global__ void __launch_bounds__(THREADS)
-ccl_merge_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims d, int* __restrict__ parent) {
-    __shared__ int2 queue[THREADS / 32][64];
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = (1u << lane) - 1u;
-    int2* q = queue[threadIdx.x >> 5];
-    int n_q = 0;                                          // warp-uniform
-    auto push = [&](bool has, int a, int b) {            // called by all lanes of the warp
-        const unsigned bits = __ballot_sync(0xffffffffu, has);
-        if (bits == 0u) return;
-        if (has) q[n_q + __popc(bits & lt)] = make_int2(a, b);
-        n_q += __popc(bits);
-        if (n_q >= 32) {
-            __syncwarp();
-            const int2 pr = q[n_q - 32 + lane];
-            n_q -= 32;
-            unite(parent, pr.x, pr.y);
-            __syncwarp();
-        }
-    };
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long base = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); base < d.total; base += stride) {
-        const long long i = base + lane;
-        const bool valid = i < d.total && mask[i] == want;
-        // a 32-voxel strip without a member of the set has nothing to link (every test below starts from `valid`):
-        // the foreground of a frangi frame is a few percent of the voxels, so most strips end here
-        if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
-        int z = 0, y = 0, x = 0;
-        if (valid) {
-            z = (int)(i / d.plane);
-            const long long rem = i - (long long)z * d.plane;
-            y = (int)(rem / d.nx);
-            x = (int)(rem - (long long)y * d.nx);
-        }
-        const int me = (int)i;
-        auto in = [&](int dz, int dy, int dx) -> bool {
-            const int zz = z + dz, yy = y + dy, xx = x + dx;
-            if (!valid || zz < 0 || yy < 0 || yy >= d.ny || xx < 0 || xx >= d.nx) return false;
-            return mask[i + (long long)dz * d.plane + (long long)dy * d.nx + dx] == want;
-        };
-        auto off = [&](int dz, int dy, int dx) -> int {
-            return (int)(i + (long long)dz * d.plane + (long long)dy * d.nx + dx);
-        };
-        const bool w_in = in(0, 0, -1);
-        push(w_in && (x & 31) == 0, me, me - 1);               // stitch 32-wide windows of one run
-        if (!FULL_CONN) {
-            // 6-/4-connectivity: link to the row above / plane above once per overlap of two runs
-            push(in(0, -1, 0) && !(w_in && in(0, -1, -1)), me, off(0, -1, 0));
-            push(in(-1, 0, 0) && !(w_in && in(-1, 0, -1)), me, off(-1, 0, 0));
-        } else {
-            // 26-/8-connectivity, backward half, ONE union per overlap of two x-runs: my run [a,b] touches every
-            // run of a backward row that meets [a-1, b+1].  Such a run either covers a-1 or a (linked by the first
-            // voxel of my run) or starts at s in [a+1, b+1] (linked by my voxel s-1, which sees the start diagonally).
-#pragma unroll
-            for (int dz = -1; dz <= 0; ++dz) {
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                    if (dz == 0 && dy >= 0) continue;          // same plane: only the row above
-                    const bool c0 = in(dz, dy, 0);
-                    const bool cp = in(dz, dy, 1), cm = in(dz, dy, -1);
-                    push(valid && !c0 && cp, me, off(dz, dy, 1));
-                    push(valid && !w_in && (c0 || cm), me, c0 ? off(dz, dy, 0) : off(dz, dy, -1));
-                }
-            }
-        }
-        if (BORDER_OUTSIDE) {
-            const bool edge = z == 0 || z == d.nz - 1 || y == 0 || y == d.ny - 1 || x == 0 || x == d.nx - 1;
-            push(valid && edge, me, OUTSIDE);
-        }
-    }
-    __syncwarp();
-    if (lane < n_q) unite(parent, q[lane].x, q[lane].y);
-}
-
-// One warp per 32-voxel strip of a row.  After ccl_init every voxel of an x-run inside the strip points at the run's
-// first voxel, so only that voxel (parent outside the strip, or itself) has to chase pointers; the rest of the run takes
-// the root from its lane by shuffle.  (One find per voxel cost 1.8 ms per pass of a 512^3 frame, three passes per frame.)
-__global__ void __launch_bounds__(THREADS)
-ccl_flatten_kernel(Dims d, int* __restrict__ parent) {
-    const int wpr = (d.nx + 31) / 32;
-    const long long nwin = (long long)d.nz * d.ny * wpr;
-    const int lane = threadIdx.x & 31;
-    for (long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; w < nwin;
-         w += ((long long)gridDim.x * blockDim.x) >> 5) {
-        const long long row = w / wpr;
-        const int x = (int)(w - row * wpr) * 32 + lane;
-        const long long idx = row * d.nx + x;
-        const long long first = idx - lane;                    // index of the strip's first voxel
-        const int p = x < d.nx ? ld_parent(parent, idx) : NOT_IN_SET;
-        // a voxel whose parent is another voxel of this strip (its run head, possibly re-linked by path halving to any
-        // ancestor inside the strip) copies that lane's result; chains inside a strip only point backwards
-        const bool local = p != NOT_IN_SET && p >= 0 && (long long)p >= first && (long long)p < idx;
-        int r = p;
-        if (p != NOT_IN_SET && !local) r = find_root_ro(parent, (int)idx);
-        // resolve local links: at most 5 rounds (a chain of backward links inside 32 lanes halves... each round follows
-        // one link, the lanes it lands on are final after as many rounds as the chain is long; chains are short (run
-        // head, or one halving step), loop until no lane changes
-        unsigned pending = __ballot_sync(0xffffffffu, local);
-        int src = local ? (int)((long long)p - first) : lane;
-        while (pending) {
-            const int rr = __shfl_sync(0xffffffffu, r, src);
-            const bool src_pending = (pending >> src) & 1u;
-            if (local && ((pending >> lane) & 1u) && !src_pending) r = rr;
-            const unsigned now = __ballot_sync(0xffffffffu, local && ((pending >> lane) & 1u) && src_pending);
-            if (now == pending) break;                           // cannot happen (links point backwards); never spin
-            pending = now;
-        }
-        if (p != NOT_IN_SET && x < d.nx) parent[idx] = r;
-    }
-}
-
-// ---- tiled CCL (round 2) ---------------------------------------------------------------------------
-// A CTA resolves one tile of 32 x TY x TZ voxels in shared memory (row = one 32-bit word of membership bits, the
-// union-find runs on local indices with shared-memory atomics), and writes every voxel's parent as the GLOBAL index of
-// its tile-local root (raster order inside a tile agrees with the global raster order, so the local root is the
-// component's first voxel there).  ccl_border_kernel then makes only the unions that cross a tile face — the rule of
-// ccl_merge_kernel restricted to pairs in different tiles — and ccl_flatten_tile_kernel resolves tile roots first and
-// everything else in one or two cached hops.  Measured on the 512^3 frame of config #5: init + merge + flatten
-// 0.36 + 1.53 + 0.9 ms per labelling before (the global atomics' latency, not the scan, was the cost).
+// ---- tiled CCL ------------------------------------------------------------------------------------
+// A CTA resolves one tile of 32 x TY x TZ voxels in shared memory (TY * TZ = 64 rows = 64 membership words; the
+// union-find runs on local indices with shared-memory atomics) and writes every voxel's parent as the GLOBAL index of
+// its tile-local root (raster order inside a tile agrees with the global raster order, so a local root is the first
+// voxel of its piece).  The unions are found on whole words, one thread per (row, backward neighbour row):
+//   26-conn, ONE union per overlap of two x-runs: my run [a, b] touches every run of a backward row that meets
+//   [a-1, b+1]; such a run either covers a-1 or a (linked by the first voxel of my run: m2) or starts at s in
+//   [a+1, b+1] (linked by my voxel s-1, which sees the start diagonally: m1)
+//   6-conn: the first voxel of every overlap of two runs
+// ccl_border_kernel then makes the unions that cross a tile face with the same rules on global indices, and
+// ccl_flatten_tile_kernel resolves the tile roots first and everything else in one or two cached hops.
+// History (512^3 frame of config #5, per labelling): voxel-wise init + merge + flatten with global atomics 2.8 ms;
+// this tile scheme with per-lane bit tests on byte masks 2.9 ms (the bit fiddling, 26 K warp instructions per tile);
+// word-wise as below: see DESIGN.md.
 __device__ __forceinline__ int find_s(int* par, int x) {
     if (x < 0) return x;
     int p = *reinterpret_cast<const volatile int*>(par + x);
@@ -286,11 +197,11 @@ struct TileGrid {
 
 template <int TY, int TZ, bool FULL_CONN, bool BORDER_OUTSIDE>
 __global__ void __launch_bounds__(THREADS)
-ccl_tile_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims d, TileGrid tg, int* __restrict__ parent,
+ccl_tile_kernel(const unsigned* __restrict__ set_bits, unsigned char want, Dims d, TileGrid tg, int* __restrict__ parent,
                 unsigned* __restrict__ root_bits, int* __restrict__ area) {
     constexpr int ROWS = TY * TZ;
     constexpr int NW = THREADS / 32;
-    static_assert(ROWS * 32 <= 32768, "local indices are queued as 16-bit values");
+    static_assert(ROWS == 64 && THREADS == 256, "one thread per (row, backward neighbour row)");
     __shared__ unsigned bits[ROWS];
     __shared__ int par[ROWS * 32];
     __shared__ int cnt[ROWS * 32];
@@ -302,23 +213,20 @@ ccl_tile_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims
     const int x0 = tx * 32, y0 = ty * TY, z0 = tz * TZ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    const int x = x0 + lane;
+    const int plane = d.ny * d.nx;
     // ---- membership words and x-runs ----
-    unsigned char mv[ROWS / NW];
-#pragma unroll
-    for (int k = 0; k < ROWS / NW; ++k) {                  // all loads in flight before the first ballot
-        const int r = warp + k * NW;
+    if (threadIdx.x < ROWS) {
+        const int r = threadIdx.x;
         const int z = z0 + r / TY, y = y0 + r % TY;
-        mv[k] = (x < d.nx && y < d.ny && z < d.nz) ? mask[(long long)z * d.plane + (long long)y * d.nx + x] : (unsigned char)(want ^ 1);
+        bits[r] = (y < d.ny && z < d.nz) ? set_word(set_bits, d, tg.tiles_x, z * d.ny + y, tx, want) : 0u;
     }
+    __syncthreads();
 #pragma unroll
     for (int k = 0; k < ROWS / NW; ++k) {
         const int r = warp + k * NW;
-        const bool in = mv[k] == want;
-        const unsigned w = __ballot_sync(0xffffffffu, in);
-        if (lane == 0) bits[r] = w;
+        const unsigned w = bits[r];
         int val = NOT_IN_SET;
-        if (in) {
+        if ((w >> lane) & 1u) {
             const unsigned below_zero = ~w & lt;
             val = r * 32 + (below_zero ? 32 - __clz(below_zero) : 0);
         }
@@ -326,67 +234,88 @@ ccl_tile_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims
         cnt[r * 32 + lane] = 0;
     }
     __syncthreads();
-    // ---- unions, found in lock step and carried out 32 at a time (see ccl_merge_kernel) ----
-    unsigned* q = queue[warp];
-    int n_q = 0;                                           // warp-uniform
-    auto push = [&](bool has, int a, int b) {             // called by all lanes; b may be OUTSIDE
-        const unsigned hb = __ballot_sync(0xffffffffu, has);
-        if (hb == 0u) return;
-        if (has) q[n_q + __popc(hb & lt)] = (unsigned)a | ((unsigned)b << 16);
-        n_q += __popc(hb);
-        if (n_q >= 32) {
-            __syncwarp();
-            const unsigned v = q[n_q - 32 + lane];
-            n_q -= 32;
-            unite_s(par, (int)(v & 0xffffu), (int)(short)(v >> 16));
-            __syncwarp();
-        }
-    };
-#pragma unroll 1
-    for (int r = warp; r < ROWS; r += NW) {
+    // ---- unions: thread = (row r, backward neighbour row q) finds them as bit masks; the warp carries them out 32 at a
+    // time from a shared queue (a thread walking its own bits alone left 2 of 32 lanes active) ----
+    {
+        unsigned* q_ = queue[warp];
+        int n_q = 0;                                        // warp-uniform
+        auto push = [&](bool has, int a, int b) {          // called by all lanes; b may be OUTSIDE
+            const unsigned hb = __ballot_sync(0xffffffffu, has);
+            if (hb == 0u) return;
+            if (has) q_[n_q + __popc(hb & lt)] = (unsigned)a | ((unsigned)b << 16);
+            n_q += __popc(hb);
+            if (n_q >= 32) {
+                __syncwarp();
+                const unsigned v = q_[n_q - 32 + lane];
+                n_q -= 32;
+                unite_s(par, (int)(v & 0xffffu), (int)(short)(v >> 16));
+                __syncwarp();
+            }
+        };
+        const int r = threadIdx.x & (ROWS - 1), q = threadIdx.x / ROWS;      // q in 0..3, uniform per warp
         const unsigned w = bits[r];
-        if (w == 0u) continue;
         const int lz = r / TY, ly = r % TY;
-        const bool me = (w >> lane) & 1u;
-        const bool w_in = lane > 0 && ((w >> (lane - 1)) & 1u);
-        const int idx = r * 32 + lane;
-        if (!FULL_CONN) {
-            if (ly > 0) {
-                const unsigned nb = bits[r - 1];
-                push(me && ((nb >> lane) & 1u) && !(w_in && ((nb >> (lane - 1)) & 1u)), idx, idx - 32);
-            }
-            if (lz > 0) {
-                const unsigned nb = bits[r - TY];
-                push(me && ((nb >> lane) & 1u) && !(w_in && ((nb >> (lane - 1)) & 1u)), idx, idx - TY * 32);
-            }
+        int dz, dy;
+        bool active;
+        if (FULL_CONN) {                                    // (0,-1), (-1,-1), (-1,0), (-1,+1)
+            dz = q == 0 ? 0 : -1;
+            dy = q == 0 ? -1 : q - 2;
+            active = true;
+        } else {                                            // (0,-1), (-1,0); q = 2: the frame border
+            dz = q == 0 ? 0 : -1;
+            dy = q == 0 ? -1 : 0;
+            active = q < 2;
+        }
+        active = active && w != 0u && lz + dz >= 0 && ly + dy >= 0 && ly + dy < TY;   // else another tile: ccl_border_kernel
+        const int rr = active ? r + dz * TY + dy : r;
+        const unsigned nb = active ? bits[rr] : 0u;
+        unsigned m1, m2;
+        if (FULL_CONN) {
+            m1 = w & ~nb & (nb >> 1);
+            m2 = w & ~(w << 1) & (nb | (nb << 1));
         } else {
-#pragma unroll
-            for (int dz = -1; dz <= 0; ++dz) {
-#pragma unroll
-                for (int dy = -1; dy <= 1; ++dy) {
-                    if (dz == 0 && dy >= 0) continue;
-                    if (lz + dz < 0 || ly + dy < 0 || ly + dy >= TY) continue;       // another tile: ccl_face_kernel
-                    const int rr = r + dz * TY + dy;
-                    const unsigned nb = bits[rr];
-                    if (nb == 0u) continue;
-                    const bool c0 = (nb >> lane) & 1u;
-                    const bool cp = lane < 31 && ((nb >> (lane + 1)) & 1u);
-                    const bool cm = lane > 0 && ((nb >> (lane - 1)) & 1u);
-                    push(me && !c0 && cp, idx, rr * 32 + lane + 1);
-                    push(me && !w_in && (c0 || cm), idx, c0 ? rr * 32 + lane : rr * 32 + lane - 1);
-                }
+            m1 = w & nb & ~((w << 1) & (nb << 1));
+            m2 = 0u;
+        }
+        if (!active) m1 = m2 = 0u;
+        while (__any_sync(0xffffffffu, m1 != 0u)) {
+            const bool has = m1 != 0u;
+            const int b = has ? __ffs(m1) - 1 : 0;
+            m1 &= m1 - 1u;
+            push(has, r * 32 + b, FULL_CONN ? rr * 32 + b + 1 : rr * 32 + b);
+        }
+        if (FULL_CONN) {
+            while (__any_sync(0xffffffffu, m2 != 0u)) {
+                const bool has = m2 != 0u;
+                const int b = has ? __ffs(m2) - 1 : 0;
+                m2 &= m2 - 1u;
+                push(has, r * 32 + b, ((nb >> b) & 1u) ? rr * 32 + b : rr * 32 + b - 1);
             }
         }
         if (BORDER_OUTSIDE) {
-            const int z = z0 + lz, y = y0 + ly;
-            const bool edge = z == 0 || z == d.nz - 1 || y == 0 || y == d.ny - 1 || x == 0 || x == d.nx - 1;
-            push(me && edge, idx, OUTSIDE);
+            // members on the frame border hang under OUTSIDE: one union per x-run of a border row, else the two ends
+            unsigned m = 0u;
+            if (q == 2 && w != 0u) {
+                const int z = z0 + lz, y = y0 + ly;
+                if (z == 0 || z == d.nz - 1 || y == 0 || y == d.ny - 1) m = w & ~(w << 1);
+                else {
+                    if (x0 == 0) m |= w & 1u;
+                    const int last = d.nx - 1 - x0;
+                    if (last >= 0 && last < 32) m |= w & (1u << last);
+                }
+            }
+            while (__any_sync(0xffffffffu, m != 0u)) {
+                const bool has = m != 0u;
+                const int b = has ? __ffs(m) - 1 : 0;
+                m &= m - 1u;
+                push(has, r * 32 + b, OUTSIDE);
+            }
         }
-    }
-    __syncwarp();
-    if (lane < n_q) {
-        const unsigned v = q[lane];
-        unite_s(par, (int)(v & 0xffffu), (int)(short)(v >> 16));
+        __syncwarp();
+        if (lane < n_q) {
+            const unsigned v = q_[lane];
+            unite_s(par, (int)(v & 0xffffu), (int)(short)(v >> 16));
+        }
     }
     __syncthreads();
     // ---- tile-local roots (and, for the size filter, voxels per local component, counted run by run) ----
@@ -405,6 +334,7 @@ ccl_tile_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims
         }
     }
     if (area != nullptr) __syncthreads();
+    const int x = x0 + lane;
 #pragma unroll
     for (int k = 0; k < ROWS / NW; ++k) {
         const int r = warp + k * NW;
@@ -414,123 +344,117 @@ ccl_tile_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims
         const bool is_root = out == r * 32 + lane;
         if (out >= 0) {
             const int rr = out >> 5;
-            out = (int)((long long)(z0 + rr / TY) * d.plane + (long long)(y0 + rr % TY) * d.nx + x0 + (out & 31));
+            out = (z0 + rr / TY) * plane + (y0 + rr % TY) * d.nx + x0 + (out & 31);
         }
         const unsigned rb = __ballot_sync(0xffffffffu, is_root);
-        if (lane == 0) root_bits[((long long)z * d.ny + y) * tg.tiles_x + tx] = rb;
+        if (lane == 0) root_bits[(long long)(z * d.ny + y) * tg.tiles_x + tx] = rb;
         if (x < d.nx) {
-            const long long i = (long long)z * d.plane + (long long)y * d.nx + x;
+            const int i = z * plane + y * d.nx + x;
             parent[i] = out;
             if (area != nullptr && is_root) area[i] = cnt[r * 32 + lane];
         }
     }
 }
 
-// unions across tile faces.  Completeness: two 26-adjacent voxels u (row r) and v (backward row r', or the same row)
-// in different tiles are either
-//   * in rows of different tiles (r' lies across a Y or Z face): the rule of ccl_merge_kernel for that row pair, all
-//     lanes (ccl_face_kernel: one warp per row that has such a neighbour row, nothing else is touched), or
-//   * in rows of one tile, in adjacent 32-wide strips (ccl_seam_x_kernel, one THREAD per strip boundary xb):
+// unions across tile faces, one THREAD per membership word (row, xw).  Completeness: two adjacent voxels u (row r) and
+// v (a backward row r', or the same row) in different tiles are either
+//   * in rows of different tiles (r' lies across a Y or Z face): the run-overlap rules of the tile kernel on the global
+//     rows, x-neighbour bits taken from the adjacent words, or
+//   * in rows of one tile, in adjacent 32-wide strips.  Then at the strip boundary xb = 32 xw:
 //       same row:            (r, xb) ~ (r, xb-1)                                       the stitch of an x-run
 //       u = (r, xb-1), v = (r', xb):   needed only if (r', xb-1) is not set (else u ~ (r', xb-1) inside the tile and
 //                                      (r', xb-1) ~ v by the stitch)
 //       u = (r, xb),   v = (r', xb-1): needed only if neither (r', xb) nor (r, xb-1) is set (same argument)
 template <int TY, int TZ, bool FULL_CONN>
 __global__ void __launch_bounds__(THREADS)
-ccl_face_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims d, int* __restrict__ parent) {
+ccl_border_kernel(const unsigned* __restrict__ set_bits, unsigned char want, Dims d, int* __restrict__ parent) {
     __shared__ int2 queue[THREADS / 32][64];
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
-    int2* q = queue[threadIdx.x >> 5];
-    int n_q = 0;                                          // warp-uniform
-    auto push = [&](bool has, int a, int b) {            // called by all lanes of the warp
-        const unsigned bits = __ballot_sync(0xffffffffu, has);
-        if (bits == 0u) return;
-        if (has) q[n_q + __popc(bits & lt)] = make_int2(a, b);
-        n_q += __popc(bits);
+    int2* q_ = queue[threadIdx.x >> 5];
+    int n_q = 0;                                            // warp-uniform
+    auto push = [&](bool has, int a, int b) {              // called by all lanes of the warp
+        const unsigned hb = __ballot_sync(0xffffffffu, has);
+        if (hb == 0u) return;
+        if (has) q_[n_q + __popc(hb & lt)] = make_int2(a, b);
+        n_q += __popc(hb);
         if (n_q >= 32) {
             __syncwarp();
-            const int2 pr = q[n_q - 32 + lane];
+            const int2 pr = q_[n_q - 32 + lane];
             n_q -= 32;
             unite(parent, pr.x, pr.y);
             __syncwarp();
         }
     };
-    const int nrows = d.nz * d.ny;                        // < 2^31 (one voxel per row at least)
     const int wpr = (d.nx + 31) / 32;
-    for (int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5); row < nrows;
-         row += (int)(((long long)gridDim.x * blockDim.x) >> 5)) {
+    const int nwords = d.nz * d.ny * wpr;
+    const int plane = d.ny * d.nx;
+    const int stride = (int)min((long long)gridDim.x * blockDim.x, 2147483647LL - nwords);
+    for (int base = (int)(blockIdx.x * (long long)blockDim.x + threadIdx.x) - lane; base < nwords; base += stride) {
+        const int wi = base + lane;
+        bool live = wi < nwords;
+        const int row = live ? wi / wpr : 0, xw = live ? wi - row * wpr : 0;
         const int z = row / d.ny, y = row - z * d.ny;
         const bool up_y = (y % TY) == 0 && y > 0, dn_y = (y % TY) == TY - 1 && y + 1 < d.ny, up_z = (z % TZ) == 0 && z > 0;
-        if (!up_y && !up_z && !(FULL_CONN && dn_y && z > 0)) continue;
-        for (int xw = 0; xw < wpr; ++xw) {
-            const int x = xw * 32 + lane;
-            const long long i = (long long)row * d.nx + x;
-            const bool valid = x < d.nx && mask[i] == want;
-            if (__ballot_sync(0xffffffffu, valid) == 0u) continue;
-            const int me = (int)i;
-            auto in = [&](int dz, int dy, int dx) -> bool {
-                const int zz = z + dz, yy = y + dy, xx = x + dx;
-                if (!valid || zz < 0 || yy < 0 || yy >= d.ny || xx < 0 || xx >= d.nx) return false;
-                return mask[i + (long long)dz * d.plane + (long long)dy * d.nx + dx] == want;
-            };
-            auto off = [&](int dz, int dy, int dx) -> int {
-                return (int)(i + (long long)dz * d.plane + (long long)dy * d.nx + dx);
-            };
-            const bool w_in = in(0, 0, -1);
-            if (!FULL_CONN) {
-                if (up_y) push(in(0, -1, 0) && !(w_in && in(0, -1, -1)), me, off(0, -1, 0));
-                if (up_z) push(in(-1, 0, 0) && !(w_in && in(-1, 0, -1)), me, off(-1, 0, 0));
-            } else {
+        live = live && (xw > 0 || up_y || up_z || (FULL_CONN && dn_y && z > 0));
+        unsigned w = 0u, w_prev = 0u;
+        if (live) {
+            w = set_word(set_bits, d, wpr, row, xw, want);
+            if (xw > 0) w_prev = set_word(set_bits, d, wpr, row, xw - 1, want) >> 31;              // (row, xb - 1)
+        }
+        live = live && (w | w_prev) != 0u;
+        if (!__any_sync(0xffffffffu, live)) continue;
+        const int i0 = row * d.nx + xw * 32;                        // voxel (row, xb)
+        push(live && (w & 1u) && w_prev, i0, i0 - 1);
 #pragma unroll
-                for (int dz = -1; dz <= 0; ++dz) {
+        for (int dz = -1; dz <= 0; ++dz) {
 #pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        if (dz == 0 && dy >= 0) continue;
-                        const bool rc = (dz < 0 && up_z) || (dy < 0 && up_y) || (dy > 0 && dn_y);   // row in another tile
-                        if (!rc) continue;
-                        const bool c0 = in(dz, dy, 0), cp = in(dz, dy, 1), cm = in(dz, dy, -1);
-                        push(valid && !c0 && cp, me, off(dz, dy, 1));
-                        push(valid && !w_in && (c0 || cm), me, c0 ? off(dz, dy, 0) : off(dz, dy, -1));
+            for (int dy = -1; dy <= 1; ++dy) {
+                if (dz == 0 && dy >= 0) continue;
+                if (!FULL_CONN && dz != 0 && dy != 0) continue;     // 6-conn: (0,-1) and (-1,0) only
+                const bool rc = (dz < 0 && up_z) || (dy < 0 && up_y) || (dy > 0 && dn_y);   // the row lies in another tile
+                const bool on = live && z + dz >= 0 && y + dy >= 0 && y + dy < d.ny && (rc || (FULL_CONN && xw > 0));
+                unsigned nb = 0u, nb_prev = 0u, nb_next = 0u;
+                if (on) {
+                    const int nrow = row + dz * d.ny + dy;
+                    nb = set_word(set_bits, d, wpr, nrow, xw, want);
+                    if (xw > 0) nb_prev = set_word(set_bits, d, wpr, nrow, xw - 1, want) >> 31;
+                    if (FULL_CONN && rc && xw + 1 < wpr) nb_next = set_word(set_bits, d, wpr, nrow, xw + 1, want) & 1u;
+                }
+                const int j0 = i0 + dz * plane + dy * d.nx;          // voxel (nrow, xb)
+                if (FULL_CONN) {                                     // one tile: the two diagonals over the strip boundary
+                    push(on && !rc && w_prev && (nb & 1u) && !nb_prev, i0 - 1, j0);
+                    push(on && !rc && (w & 1u) && nb_prev && !(nb & 1u) && !w_prev, i0, j0 - 1);
+                }
+                unsigned m1 = 0u, m2 = 0u;
+                if (on && rc) {
+                    const unsigned cm = (nb << 1) | nb_prev, w_in = (w << 1) | w_prev;
+                    if (FULL_CONN) {
+                        m1 = w & ~nb & ((nb >> 1) | (nb_next << 31));
+                        m2 = w & ~w_in & (nb | cm);
+                    } else {
+                        m1 = w & nb & ~(w_in & cm);
+                    }
+                }
+                while (__any_sync(0xffffffffu, m1 != 0u)) {
+                    const bool has = m1 != 0u;
+                    const int b = has ? __ffs(m1) - 1 : 0;
+                    m1 &= m1 - 1u;
+                    push(has, i0 + b, FULL_CONN ? j0 + b + 1 : j0 + b);
+                }
+                if (FULL_CONN) {
+                    while (__any_sync(0xffffffffu, m2 != 0u)) {
+                        const bool has = m2 != 0u;
+                        const int b = has ? __ffs(m2) - 1 : 0;
+                        m2 &= m2 - 1u;
+                        push(has, i0 + b, ((nb >> b) & 1u) ? j0 + b : j0 + b - 1);
                     }
                 }
             }
         }
     }
     __syncwarp();
-    if (lane < n_q) unite(parent, q[lane].x, q[lane].y);
-}
-
-template <int TY, int TZ, bool FULL_CONN>
-__global__ void __launch_bounds__(THREADS)
-ccl_seam_x_kernel(const unsigned char* __restrict__ mask, unsigned char want, Dims d, int* __restrict__ parent) {
-    const int nb = (d.nx - 1) / 32;                       // strip boundaries per row: xb = 32, 64, ... < nx
-    if (nb <= 0) return;
-    const long long total = (long long)d.nz * d.ny * nb;
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-        const int row = (int)(k / nb);
-        const int xb = ((int)(k - (long long)row * nb) + 1) * 32;
-        const long long i = (long long)row * d.nx + xb;          // voxel (row, xb); i - 1 = (row, xb - 1)
-        const bool e = mask[i] == want, w = mask[i - 1] == want;
-        if (!e && !w) continue;
-        if (e && w) unite(parent, (int)i, (int)i - 1);
-        if (!FULL_CONN) continue;
-        const int z = row / d.ny, y = row - z * d.ny;
-        const bool up_y = (y % TY) == 0, dn_y = (y % TY) == TY - 1, up_z = (z % TZ) == 0;
-#pragma unroll
-        for (int dz = -1; dz <= 0; ++dz) {
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                if (dz == 0 && dy >= 0) continue;
-                if ((dz < 0 && up_z) || (dy < 0 && up_y) || (dy > 0 && dn_y)) continue;   // ccl_face_kernel's pair
-                if (z + dz < 0 || y + dy < 0 || y + dy >= d.ny) continue;
-                const long long j = i + (long long)dz * d.plane + (long long)dy * d.nx;   // (r', xb)
-                const bool ne = mask[j] == want, nw = mask[j - 1] == want;
-                if (w && ne && !nw) unite(parent, (int)i - 1, (int)j);
-                if (e && nw && !ne && !w) unite(parent, (int)i, (int)j - 1);
-            }
-        }
-    }
+    if (lane < n_q) unite(parent, q_[lane].x, q_[lane].y);
 }
 
 // parent[i] = root of i for every voxel of the set.  root_bits (one word per 32-voxel strip row, written by the tile
@@ -549,16 +473,17 @@ ccl_flatten_tile_kernel(Dims d, TileGrid tg, const unsigned* __restrict__ root_b
     const int x0 = tx * 32, y0 = ty * TY, z0 = tz * TZ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int x = x0 + lane;
+    const int plane = d.ny * d.nx;
 #pragma unroll
     for (int k = 0; k < ROWS / (THREADS / 32); ++k) {
         const int r = warp + k * (THREADS / 32);
         const int z = z0 + r / TY, y = y0 + r % TY;
         if (y >= d.ny || z >= d.nz) continue;
-        const unsigned rb = __ldg(root_bits + ((long long)z * d.ny + y) * tg.tiles_x + tx);
+        const unsigned rb = __ldg(root_bits + (long long)(z * d.ny + y) * tg.tiles_x + tx);
         if (!((rb >> lane) & 1u)) continue;
-        const long long i = (long long)z * d.plane + (long long)y * d.nx + x;
+        const int i = z * plane + y * d.nx + x;
         const int p = ld_parent(parent, i);
-        if (p >= 0 && p != (int)i) {
+        if (p >= 0 && p != i) {
             const int f = find_root_ro(parent, p);
             parent[i] = f;
             // the size of a component is the sum over its tile-local pieces; area[i] of a non-root is final (nobody adds to it)
@@ -571,9 +496,9 @@ ccl_flatten_tile_kernel(Dims d, TileGrid tg, const unsigned* __restrict__ root_b
         const int r = warp + k * (THREADS / 32);
         const int z = z0 + r / TY, y = y0 + r % TY;
         if (x >= d.nx || y >= d.ny || z >= d.nz) continue;
-        const long long i = (long long)z * d.plane + (long long)y * d.nx + x;
+        const int i = z * plane + y * d.nx + x;
         const int p = ld_parent(parent, i);
-        if (p < 0 || p == (int)i) continue;
+        if (p < 0 || p == i) continue;
         const int q = ld_parent(parent, p);
         if (q != p) parent[i] = find_root_ro(parent, q);       // q == p: p is a root and parent[i] is final already
     }
@@ -581,36 +506,23 @@ ccl_flatten_tile_kernel(Dims d, TileGrid tg, const unsigned* __restrict__ root_b
 
 // ---- fill holes: mask |= background voxels whose tree is not tied to OUTSIDE ----------------------
 __global__ void __launch_bounds__(THREADS)
-fill_holes_kernel(Dims d, const int* __restrict__ parent, unsigned char* __restrict__ mask) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int p = parent[i];            // flattened: root index, OUTSIDE, or NOT_IN_SET (foreground)
-        if (p >= 0) mask[i] = 1;
+fill_holes_bits_kernel(Dims d, const int* __restrict__ parent, unsigned* __restrict__ bits) {
+    const int wpr = (d.nx + 31) / 32;
+    const int nwin = d.nz * d.ny * wpr;
+    const int lane = threadIdx.x & 31;
+    for (int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5); w < nwin;
+         w += (int)(((long long)gridDim.x * blockDim.x) >> 5)) {
+        const int row = w / wpr;
+        const int x = (w - row * wpr) * 32 + lane;
+        // flattened background labelling: root index (a hole), OUTSIDE, or NOT_IN_SET (foreground)
+        const bool hole = x < d.nx && parent[(long long)row * d.nx + x] >= 0;
+        const unsigned b = __ballot_sync(0xffffffffu, hole);
+        if (lane == 0 && b) bits[w] |= b;
     }
 }
 
-// ---- component sizes -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS)
-area_count_kernel(Dims d, const int* __restrict__ parent, int* __restrict__ area) {
-    // consecutive voxels with the same root (x-runs, after the flatten) are counted once: the first lane of each group
-    // adds the group's length
-    for (long long base = blockIdx.x * (long long)blockDim.x; base < d.total; base += (long long)gridDim.x * blockDim.x) {
-        const long long i = base + threadIdx.x;
-        const int lane = threadIdx.x & 31;
-        const int r = i < d.total ? parent[i] : NOT_IN_SET;
-        const int prev = __shfl_up_sync(0xffffffffu, r, 1);
-        const bool head = lane == 0 || prev != r;
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        if (head && r >= 0) {
-            const unsigned later = lane == 31 ? 0u : (heads >> (lane + 1));
-            const int len = later ? __ffs(later) : 32 - lane;
-            atomicAdd(area + r, len);
-        }
-    }
-}
-
-// keep = component has at least min_area voxels, written as one membership word per 32-voxel strip of a row
-// (bit k of word [row][xw] = voxel x = 32 xw + k; bits beyond nx are 0)
+// ---- size filter ---------------------------------------------------------------------------------
+// keep = component has at least min_area voxels (area[root] comes out of the labelling itself)
 __global__ void __launch_bounds__(THREADS)
 area_keep_bits_kernel(Dims d, const int* __restrict__ parent, const int* __restrict__ area, long long min_area,
                       unsigned* __restrict__ keep_bits) {
@@ -637,14 +549,14 @@ area_keep_bits_kernel(Dims d, const int* __restrict__ parent, const int* __restr
 // planes (a 2-bit sum per voxel) and accumulated into a 5-plane counter; 32 voxels cost ~15 logic instructions per row
 // instead of 3 byte loads each (the per-voxel form took 1.5 ms of a 512^3 frame, a warp-per-strip form with shuffles 2.9).
 __global__ void __launch_bounds__(THREADS)
-majority_bits_kernel(const unsigned* __restrict__ bits, Dims d, unsigned char* __restrict__ out) {
+majority_bits_kernel(const unsigned* __restrict__ bits, Dims d, unsigned* __restrict__ out) {
     const int wpr = (d.nx + 31) / 32;
-    const long long nwords = (long long)d.nz * d.ny * wpr;
+    const int nwords = d.nz * d.ny * wpr;
     const bool three_d = d.nz > 1;
-    for (long long wi = blockIdx.x * (long long)blockDim.x + threadIdx.x; wi < nwords; wi += (long long)gridDim.x * blockDim.x) {
-        const long long row = wi / wpr;
-        const int xw = (int)(wi - row * wpr);
-        const int z = (int)(row / d.ny), y = (int)(row - (long long)z * d.ny);
+    for (int wi = (int)(blockIdx.x * (long long)blockDim.x + threadIdx.x); wi < nwords; wi += (int)((long long)gridDim.x * blockDim.x)) {
+        const int row = wi / wpr;
+        const int xw = wi - row * wpr;
+        const int z = row / d.ny, y = row - z * d.ny;
         const int nvalid = min(32, d.nx - xw * 32);
         unsigned t0 = 0u, t1 = 0u, t2 = 0u, t3 = 0u, t4 = 0u;
         for (int dz = three_d ? -1 : 0; dz <= (three_d ? 1 : 0); ++dz) {
@@ -652,7 +564,7 @@ majority_bits_kernel(const unsigned* __restrict__ bits, Dims d, unsigned char* _
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
                 const int yy = min(max(y + dy, 0), d.ny - 1);
-                const unsigned* rw = bits + ((long long)zz * d.ny + yy) * wpr;
+                const unsigned* rw = bits + (long long)(zz * d.ny + yy) * wpr;
                 unsigned c = __ldg(rw + xw);
                 const unsigned left = xw > 0 ? (__ldg(rw + xw - 1) >> 31) : (c & 1u);
                 unsigned right;
@@ -680,45 +592,40 @@ majority_bits_kernel(const unsigned* __restrict__ bits, Dims d, unsigned char* _
         }
         unsigned res = three_d ? (t4 | (t3 & t2 & t1)) : (t4 | t3 | (t2 & (t1 | t0)));
         if (nvalid < 32) res &= (1u << nvalid) - 1u;
-        unsigned char* o = out + row * d.nx + (long long)xw * 32;
-        if (nvalid == 32 && (reinterpret_cast<uintptr_t>(o) & 15u) == 0u) {
-            uint4 lo, hi;
-            lo.x = ((res >> 0) & 15u) * 0x00204081u & 0x01010101u;
-            lo.y = ((res >> 4) & 15u) * 0x00204081u & 0x01010101u;
-            lo.z = ((res >> 8) & 15u) * 0x00204081u & 0x01010101u;
-            lo.w = ((res >> 12) & 15u) * 0x00204081u & 0x01010101u;
-            hi.x = ((res >> 16) & 15u) * 0x00204081u & 0x01010101u;
-            hi.y = ((res >> 20) & 15u) * 0x00204081u & 0x01010101u;
-            hi.z = ((res >> 24) & 15u) * 0x00204081u & 0x01010101u;
-            hi.w = ((res >> 28) & 15u) * 0x00204081u & 0x01010101u;
-            reinterpret_cast<uint4*>(o)[0] = lo;
-            reinterpret_cast<uint4*>(o)[1] = hi;
-        } else {
-            for (int k = 0; k < nvalid; ++k) o[k] = (res >> k) & 1u;
-        }
+        out[wi] = res;
     }
 }
 
 // ---- raster-order numbering of the roots -------------------------------------------------------------
-constexpr int RANK_CHUNK = 2048;    // voxels per block in the counting / assigning kernels
+// A root of the final labelling is a tile-local root that no union re-linked, so only the voxels flagged in root_bits
+// are tested.  Words are in raster order; one warp counts / numbers a chunk of 32 words, a single CTA scans the chunks.
+constexpr int RANK_WORDS = 32;
+
+__device__ __forceinline__ int count_roots(unsigned rb, int i0, const int* __restrict__ parent) {
+    int c = 0;
+    while (rb) {
+        const int b = __ffs(rb) - 1;
+        rb &= rb - 1u;
+        c += parent[i0 + b] == i0 + b;
+    }
+    return c;
+}
 
 __global__ void __launch_bounds__(THREADS)
-root_count_kernel(Dims d, const int* __restrict__ parent, int* __restrict__ block_counts) {
-    __shared__ int warp_sums[THREADS / 32];
-    const long long base = (long long)blockIdx.x * RANK_CHUNK;
+root_count_kernel(Dims d, const unsigned* __restrict__ root_bits, const int* __restrict__ parent, int nwords,
+                  int* __restrict__ block_counts) {
+    const int wpr = (d.nx + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int chunk = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    const int wi = chunk * RANK_WORDS + lane;
+    if (chunk * RANK_WORDS >= nwords) return;               // warp-uniform
     int c = 0;
-    for (int k = threadIdx.x; k < RANK_CHUNK; k += THREADS) {
-        const long long i = base + k;
-        if (i < d.total && parent[i] == (int)i) ++c;
+    if (wi < nwords) {
+        const int row = wi / wpr;
+        c = count_roots(__ldg(root_bits + wi), row * d.nx + (wi - row * wpr) * 32, parent);
     }
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int s = 0;
-        for (int k = 0; k < THREADS / 32; ++k) s += warp_sums[k];
-        block_counts[blockIdx.x] = s;
-    }
+    if (lane == 0) block_counts[chunk] = c;
 }
 
 // single CTA: exclusive scan of block_counts in place; total -> *n_labels
@@ -759,32 +666,31 @@ block_scan_kernel(int* __restrict__ block_counts, long long nblocks, long long* 
 }
 
 __global__ void __launch_bounds__(THREADS)
-root_assign_kernel(Dims d, const int* __restrict__ parent, const int* __restrict__ block_offsets,
-                   int* __restrict__ labels) {
-    // ranks inside a chunk follow raster order: the chunk is scanned in THREADS-wide strips
-    __shared__ int warp_sums[THREADS / 32];
-    __shared__ int running;
-    if (threadIdx.x == 0) running = block_offsets[blockIdx.x];
-    __syncthreads();
-    const long long base = (long long)blockIdx.x * RANK_CHUNK;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int k0 = 0; k0 < RANK_CHUNK; k0 += THREADS) {
-        const long long i = base + k0 + threadIdx.x;
-        const bool is_root = i < d.total && parent[i] == (int)i;
-        const unsigned bits = __ballot_sync(0xffffffffu, is_root);
-        const int before_in_warp = __popc(bits & ((1u << lane) - 1u));
-        if (lane == 0) warp_sums[w] = __popc(bits);
-        __syncthreads();
-        int before = running;
-        for (int k = 0; k < w; ++k) before += warp_sums[k];
-        if (is_root) labels[i] = before + before_in_warp + 1;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int s = 0;
-            for (int k = 0; k < THREADS / 32; ++k) s += warp_sums[k];
-            running += s;
-        }
-        __syncthreads();
+root_assign_kernel(Dims d, const unsigned* __restrict__ root_bits, const int* __restrict__ parent, int nwords,
+                   const int* __restrict__ block_offsets, int* __restrict__ labels) {
+    const int wpr = (d.nx + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const int chunk = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+    const int wi = chunk * RANK_WORDS + lane;
+    if (chunk * RANK_WORDS >= nwords) return;               // warp-uniform
+    unsigned rb = 0u;
+    int i0 = 0;
+    if (wi < nwords) {
+        const int row = wi / wpr;
+        rb = __ldg(root_bits + wi);
+        i0 = row * d.nx + (wi - row * wpr) * 32;
+    }
+    const int c = count_roots(rb, i0, parent);
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    int next = block_offsets[chunk] + incl - c;             // roots before this word
+    while (rb) {
+        const int b = __ffs(rb) - 1;
+        rb &= rb - 1u;
+        if (parent[i0 + b] == i0 + b) labels[i0 + b] = ++next;
     }
 }
 
@@ -808,61 +714,66 @@ Dims make_dims(int nz, int ny, int nx) {
 
 unsigned gs(long long n) { return nb::grid_for(n, THREADS, 8); }
 
-long long max_ll(long long a, long long b) { return a > b ? a : b; }
 
-int run_ccl_legacy(const unsigned char* mask, unsigned char want, const Dims& d, bool full_conn, bool border_outside,
-                   int* parent, cudaStream_t st) {
-    ccl_init_kernel<<<gs(d.total), THREADS, 0, st>>>(mask, want, d, parent);
-    if (full_conn && !border_outside) ccl_merge_kernel<true, false><<<gs(d.total), THREADS, 0, st>>>(mask, want, d, parent);
-    else if (!full_conn && border_outside) ccl_merge_kernel<false, true><<<gs(d.total), THREADS, 0, st>>>(mask, want, d, parent);
-    else if (!full_conn) ccl_merge_kernel<false, false><<<gs(d.total), THREADS, 0, st>>>(mask, want, d, parent);
-    else ccl_merge_kernel<true, true><<<gs(d.total), THREADS, 0, st>>>(mask, want, d, parent);
-    ccl_flatten_kernel<<<gs(d.total), THREADS, 0, st>>>(d, parent);
-    return nb::check_launch("ccl");
-}
-
+// parent[i] = root of i (first voxel of its component in raster order), OUTSIDE or NOT_IN_SET, for the set `want` of the
+// packed mask.  area (optional): on return area[r] = voxels of the component with root r (other entries are scratch).
 template <int TY, int TZ>
-int run_ccl_tiled(const unsigned char* mask, unsigned char want, const Dims& d, bool full_conn, bool border_outside,
+int run_ccl_tiled(const unsigned* set_bits, unsigned char want, const Dims& d, bool full_conn, bool border_outside,
                   int* parent, unsigned* root_bits, int* area, cudaStream_t st) {
-    static const int stage = [] { const char* e = getenv("NB200_CCL_STAGE"); return e ? atoi(e) : 9; }();   // timing aid
     TileGrid tg;
     tg.tiles_x = (d.nx + 31) / 32;
     tg.tiles_y = (d.ny + TY - 1) / TY;
     const long long tiles = (long long)tg.tiles_x * tg.tiles_y * ((d.nz + TZ - 1) / TZ);
     NB_REQUIRE(tiles < 2147483647LL, NB200_ERR_UNSUPPORTED, "ccl: too many tiles");
     const unsigned g = (unsigned)tiles;
-    if (full_conn && !border_outside) ccl_tile_kernel<TY, TZ, true, false><<<g, THREADS, 0, st>>>(mask, want, d, tg, parent, root_bits, area);
-    else if (!full_conn && border_outside) ccl_tile_kernel<TY, TZ, false, true><<<g, THREADS, 0, st>>>(mask, want, d, tg, parent, root_bits, area);
-    else if (!full_conn) ccl_tile_kernel<TY, TZ, false, false><<<g, THREADS, 0, st>>>(mask, want, d, tg, parent, root_bits, area);
-    else ccl_tile_kernel<TY, TZ, true, true><<<g, THREADS, 0, st>>>(mask, want, d, tg, parent, root_bits, area);
-    if (stage < 2) return nb::check_launch("ccl(tiled)");
-    const long long rows = (long long)d.nz * d.ny;
-    const long long seams = rows * ((d.nx - 1) / 32);
-    if (full_conn) {
-        if (seams > 0) ccl_seam_x_kernel<TY, TZ, true><<<gs(seams), THREADS, 0, st>>>(mask, want, d, parent);
-        if (stage >= 3) ccl_face_kernel<TY, TZ, true><<<gs(rows * 32), THREADS, 0, st>>>(mask, want, d, parent);
-    } else {
-        if (seams > 0) ccl_seam_x_kernel<TY, TZ, false><<<gs(seams), THREADS, 0, st>>>(mask, want, d, parent);
-        if (stage >= 3) ccl_face_kernel<TY, TZ, false><<<gs(rows * 32), THREADS, 0, st>>>(mask, want, d, parent);
-    }
-    if (stage < 4) return nb::check_launch("ccl(tiled)");
+    const long long words = (long long)d.nz * d.ny * tg.tiles_x;
+    if (full_conn && !border_outside) ccl_tile_kernel<TY, TZ, true, false><<<g, THREADS, 0, st>>>(set_bits, want, d, tg, parent, root_bits, area);
+    else if (!full_conn && border_outside) ccl_tile_kernel<TY, TZ, false, true><<<g, THREADS, 0, st>>>(set_bits, want, d, tg, parent, root_bits, area);
+    else if (!full_conn) ccl_tile_kernel<TY, TZ, false, false><<<g, THREADS, 0, st>>>(set_bits, want, d, tg, parent, root_bits, area);
+    else ccl_tile_kernel<TY, TZ, true, true><<<g, THREADS, 0, st>>>(set_bits, want, d, tg, parent, root_bits, area);
+    if (full_conn) ccl_border_kernel<TY, TZ, true><<<gs(words), THREADS, 0, st>>>(set_bits, want, d, parent);
+    else ccl_border_kernel<TY, TZ, false><<<gs(words), THREADS, 0, st>>>(set_bits, want, d, parent);
     ccl_flatten_tile_kernel<TY, TZ><<<g, THREADS, 0, st>>>(d, tg, root_bits, parent, area);
-    return nb::check_launch("ccl(tiled)");
+    return nb::check_launch("ccl");
 }
 
-// area (optional): on return area[r] = voxels of the component with root r (other entries are scratch)
-int run_ccl(const unsigned char* mask, unsigned char want, const Dims& d, bool full_conn, bool border_outside,
+int run_ccl(const unsigned* set_bits, unsigned char want, const Dims& d, bool full_conn, bool border_outside,
             int* parent, unsigned* root_bits, int* area, cudaStream_t st) {
-    static const int legacy = [] { const char* e = getenv("NB200_CCL_LEGACY"); return e ? atoi(e) : 0; }();
-    if (legacy) {
-        const int rc = run_ccl_legacy(mask, want, d, full_conn, border_outside, parent, st);
-        if (rc || area == nullptr) return rc;
-        cudaMemsetAsync(area, 0, sizeof(int) * d.total, st);
-        area_count_kernel<<<gs(d.total), THREADS, 0, st>>>(d, parent, area);
-        return nb::check_launch("area_count");
-    }
-    if (d.nz > 1) return run_ccl_tiled<8, 8>(mask, want, d, full_conn, border_outside, parent, root_bits, area, st);
-    return run_ccl_tiled<64, 1>(mask, want, d, full_conn, border_outside, parent, root_bits, area, st);
+    if (d.nz > 1) return run_ccl_tiled<8, 8>(set_bits, want, d, full_conn, border_outside, parent, root_bits, area, st);
+    return run_ccl_tiled<64, 1>(set_bits, want, d, full_conn, border_outside, parent, root_bits, area, st);
+}
+
+struct Workspace {
+    int* parent;
+    unsigned* bits_a;
+    unsigned* bits_b;
+    int* block_counts;
+    long long words, nblocks;
+};
+
+long long al256(long long b) { return (b + 255) / 256 * 256; }
+
+// parent int32[n] | mask words u32[words] | root / keep words u32[words] | block counts int32[nblocks], 256-byte aligned
+Workspace carve(void* workspace, const Dims& d) {
+    Workspace w;
+    w.words = (long long)d.nz * d.ny * ((d.nx + 31) / 32);
+    w.nblocks = (w.words + RANK_WORDS - 1) / RANK_WORDS;
+    char* ws = static_cast<char*>(workspace);
+    w.parent = reinterpret_cast<int*>(ws);
+    w.bits_a = reinterpret_cast<unsigned*>(ws + al256(4 * d.total));
+    w.bits_b = reinterpret_cast<unsigned*>(ws + al256(4 * d.total) + al256(4 * w.words));
+    w.block_counts = reinterpret_cast<int*>(ws + al256(4 * d.total) + 2 * al256(4 * w.words));
+    return w;
+}
+
+int number_components(const Dims& d, const Workspace& w, int* labels, long long* n_labels, cudaStream_t st) {
+    // w.bits_b holds the tile-root words of the labelling that has just run
+    const unsigned ctas = (unsigned)((w.nblocks + THREADS / 32 - 1) / (THREADS / 32));
+    root_count_kernel<<<ctas, THREADS, 0, st>>>(d, w.bits_b, w.parent, (int)w.words, w.block_counts);
+    block_scan_kernel<<<1, 1024, 0, st>>>(w.block_counts, w.nblocks, n_labels);
+    root_assign_kernel<<<ctas, THREADS, 0, st>>>(d, w.bits_b, w.parent, (int)w.words, w.block_counts, labels);
+    label_propagate_kernel<<<gs(d.total), THREADS, 0, st>>>(d, w.parent, labels);
+    return nb::check_launch("number_components");
 }
 
 }  // namespace
@@ -870,13 +781,10 @@ int run_ccl(const unsigned char* mask, unsigned char want, const Dims& d, bool f
 extern "C" {
 
 size_t nb200_label_workspace_bytes(int nz, int ny, int nx) {
-    const long long n = (long long)nz * ny * nx;
-    const long long nblocks = (n + RANK_CHUNK - 1) / RANK_CHUNK;
-    // parent int32[n] | mask_a u8[n] | keep words u32[rows * ceil(nx/32)] (at least n bytes) | block counts int32[nblocks]
-    // (each 256-byte aligned)
-    auto al = [](long long b) { return (b + 255) / 256 * 256; };
+    const Dims d = make_dims(nz, ny, nx);
     const long long words = (long long)nz * ny * ((nx + 31) / 32);
-    return (size_t)(al(4 * n) + al(n) + al(max_ll(n, 4 * words)) + al(4 * nblocks));
+    const long long nblocks = (words + RANK_WORDS - 1) / RANK_WORDS;
+    return (size_t)(al256(4 * d.total) + 2 * al256(4 * words) + al256(4 * nblocks));
 }
 
 int nb200_label_frame(const float* frangi, const float* raw, int use_intensity, float intensity_thresh,
@@ -889,60 +797,41 @@ int nb200_label_frame(const float* frangi, const float* raw, int use_intensity, 
     NB_REQUIRE(n < 2147483000LL, NB200_ERR_UNSUPPORTED, "nb200_label_frame: frame exceeds int32 voxel indexing");
     const Dims d = make_dims(nz, ny, nx);
     cudaStream_t st = nb::as_stream(stream);
-    auto al = [](long long b) { return (b + 255) / 256 * 256; };
-    char* ws = static_cast<char*>(workspace);
-    int* parent = reinterpret_cast<int*>(ws);
-    unsigned char* mask_a = reinterpret_cast<unsigned char*>(ws + al(4 * n));
-    const long long words = (long long)nz * ny * ((nx + 31) / 32);
-    unsigned* keep_bits = reinterpret_cast<unsigned*>(mask_a + al(n));
-    int* block_counts = reinterpret_cast<int*>(mask_a + al(n) + al(max_ll(n, 4 * words)));
-    const long long nblocks = (n + RANK_CHUNK - 1) / RANK_CHUNK;
+    const Workspace w = carve(workspace, d);
     int rc;
 
-    threshold_mask_kernel<<<gs(n), THREADS, 0, st>>>(frangi, raw, use_intensity, intensity_thresh, thr, n, mask_a);
+    threshold_bits_kernel<<<gs(n), THREADS, 0, st>>>(frangi, raw, use_intensity, intensity_thresh, thr, d, w.bits_a);
     if (fill_holes && nz > 1) {   // labelling.py:485-486 (3-D only)
-        rc = run_ccl(mask_a, 0, d, /*full_conn=*/false, /*border_outside=*/true, parent, keep_bits, nullptr, st);
+        rc = run_ccl(w.bits_a, 0, d, /*full_conn=*/false, /*border_outside=*/true, w.parent, w.bits_b, nullptr, st);
         if (rc) return rc;
-        fill_holes_kernel<<<gs(n), THREADS, 0, st>>>(d, parent, mask_a);
+        fill_holes_bits_kernel<<<gs(n), THREADS, 0, st>>>(d, w.parent, w.bits_a);
     }
-    // first labelling + size filter (labelling.py:489-501)
-    rc = run_ccl(mask_a, 1, d, true, false, parent, keep_bits, /*area=*/labels, st);
+    // first labelling + size filter (labelling.py:489-501); the int32 output doubles as the size table
+    rc = run_ccl(w.bits_a, 1, d, true, false, w.parent, w.bits_b, /*area=*/labels, st);
     if (rc) return rc;
-    area_keep_bits_kernel<<<gs(n), THREADS, 0, st>>>(d, parent, labels, min_area, keep_bits);
+    area_keep_bits_kernel<<<gs(n), THREADS, 0, st>>>(d, w.parent, labels, min_area, w.bits_b);
     // smoothing (labelling.py:503-505) and second labelling (:507)
-    majority_bits_kernel<<<gs(words), THREADS, 0, st>>>(keep_bits, d, mask_a);
-    rc = run_ccl(mask_a, 1, d, true, false, parent, keep_bits, nullptr, st);
+    majority_bits_kernel<<<gs(w.words), THREADS, 0, st>>>(w.bits_b, d, w.bits_a);
+    rc = run_ccl(w.bits_a, 1, d, true, false, w.parent, w.bits_b, nullptr, st);
     if (rc) return rc;
-    root_count_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(d, parent, block_counts);
-    block_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, n_labels);
-    root_assign_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(d, parent, block_counts, labels);
-    label_propagate_kernel<<<gs(n), THREADS, 0, st>>>(d, parent, labels);
-    return nb::check_launch("label_frame");
+    return number_components(d, w, labels, n_labels, st);
 }
 
-/* scipy.ndimage.label(mask, structure=ones) alone (used by tests and by the Network stage later):
+/* scipy.ndimage.label(mask, structure=ones) alone (tests, the Z-sharded Label, the Network stage):
  * mask: uint8 device array; connectivity_full: 1 = 26/8, 0 = 6/4. */
 int nb200_ccl_label(const unsigned char* mask, int nz, int ny, int nx, int connectivity_full, int* labels,
                     void* workspace, long long* n_labels, void* stream) {
     NB_REQUIRE(mask && labels && workspace && n_labels, NB200_ERR_ARG, "nb200_ccl_label: null argument");
+    NB_REQUIRE(nz >= 1 && ny >= 1 && nx >= 1, NB200_ERR_ARG, "nb200_ccl_label: bad shape");
     const long long n = (long long)nz * ny * nx;
     NB_REQUIRE(n < 2147483000LL, NB200_ERR_UNSUPPORTED, "nb200_ccl_label: frame exceeds int32 voxel indexing");
     const Dims d = make_dims(nz, ny, nx);
     cudaStream_t st = nb::as_stream(stream);
-    auto al = [](long long b) { return (b + 255) / 256 * 256; };
-    char* ws = static_cast<char*>(workspace);
-    int* parent = reinterpret_cast<int*>(ws);
-    const long long words = (long long)nz * ny * ((nx + 31) / 32);
-    unsigned* root_bits = reinterpret_cast<unsigned*>(ws + al(4 * n) + al(n));
-    int* block_counts = reinterpret_cast<int*>(ws + al(4 * n) + al(n) + al(max_ll(n, 4 * words)));
-    const long long nblocks = (n + RANK_CHUNK - 1) / RANK_CHUNK;
-    int rc = run_ccl(mask, 1, d, connectivity_full != 0, false, parent, root_bits, nullptr, st);
+    const Workspace w = carve(workspace, d);
+    pack_bits_kernel<0><<<gs(n), THREADS, 0, st>>>(mask, d, w.bits_a);
+    const int rc = run_ccl(w.bits_a, 1, d, connectivity_full != 0, false, w.parent, w.bits_b, nullptr, st);
     if (rc) return rc;
-    root_count_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(d, parent, block_counts);
-    block_scan_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, n_labels);
-    root_assign_kernel<<<(unsigned)nblocks, THREADS, 0, st>>>(d, parent, block_counts, labels);
-    label_propagate_kernel<<<gs(n), THREADS, 0, st>>>(d, parent, labels);
-    return nb::check_launch("ccl_label");
+    return number_components(d, w, labels, n_labels, st);
 }
 
 }  // extern "C"
@@ -983,14 +872,6 @@ pixel_class_kernel(const int* __restrict__ skel, Dims d, unsigned char* __restri
             res = (unsigned char)(cnt > 4 ? 4 : cnt);
         }
         out[i] = res;
-    }
-}
-
-__global__ void __launch_bounds__(THREADS)
-non_junction_mask_kernel(const unsigned char* __restrict__ pixel_class, long long n, unsigned char* __restrict__ mask) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned char c = pixel_class[i];
-        mask[i] = (c > 0 && c != 4) ? 1 : 0;
     }
 }
 
@@ -1038,14 +919,16 @@ int nb200_pixel_class(const int* skel, int nz, int ny, int nx, unsigned char* ou
 int nb200_branch_labels(const unsigned char* pixel_class, int nz, int ny, int nx, int* labels, void* workspace,
                         long long* n_labels, void* stream) {
     NB_REQUIRE(pixel_class && labels && workspace && n_labels, NB200_ERR_ARG, "nb200_branch_labels: null argument");
+    NB_REQUIRE(nz >= 1 && ny >= 1 && nx >= 1, NB200_ERR_ARG, "nb200_branch_labels: bad shape");
     const long long n = (long long)nz * ny * nx;
     NB_REQUIRE(n < 2147483000LL, NB200_ERR_UNSUPPORTED, "nb200_branch_labels: frame exceeds int32 voxel indexing");
-    auto al = [](long long b) { return (b + 255) / 256 * 256; };
-    unsigned char* mask = reinterpret_cast<unsigned char*>(static_cast<char*>(workspace) + al(4 * n));   // mask_a of the label workspace
-    non_junction_mask_kernel<<<gs(n), THREADS, 0, nb::as_stream(stream)>>>(pixel_class, n, mask);
-    int rc = nb::check_launch("branch_labels(mask)");
+    const Dims d = make_dims(nz, ny, nx);
+    cudaStream_t st = nb::as_stream(stream);
+    const Workspace w = carve(workspace, d);
+    pack_bits_kernel<1><<<gs(n), THREADS, 0, st>>>(pixel_class, d, w.bits_a);        // class 1..3: not a junction
+    const int rc = run_ccl(w.bits_a, 1, d, true, false, w.parent, w.bits_b, nullptr, st);
     if (rc) return rc;
-    return nb200_ccl_label(mask, nz, ny, nx, 1, labels, workspace, n_labels, stream);
+    return number_components(d, w, labels, n_labels, st);
 }
 
 int nb200_remove_connected_label_pixels(const int* labels, int nz, int ny, int nx, int* out, void* stream) {
