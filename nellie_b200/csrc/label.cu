@@ -93,31 +93,27 @@ threshold_bits_kernel(const float* __restrict__ frangi, const float* __restrict_
     const int wpr = (d.nx + 31) / 32;
     const int nwin = d.nz * d.ny * wpr;
     const int lane = threadIdx.x & 31;
-    constexpr int U = 4;                                    // strips per warp and iteration: four loads in flight
+    constexpr int U = 8;                                    // strips per warp and iteration: eight loads in flight, one division
     const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
     for (int w0 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * U; w0 < nwin; w0 += nwarps * U) {
+        int row = w0 / wpr, xw = w0 - row * wpr;
         float f[U];
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            const int w = w0 + k;
-            const int row = w / wpr;
-            const int x = (w - row * wpr) * 32 + lane;
-            f[k] = -INFINITY;
-            if (w < nwin && x < d.nx) {
+            const int x = xw * 32 + lane;
+            f[k] = -INFINITY;                               // outside the frame: never above the cut
+            if (w0 + k < nwin && x < d.nx) {
                 const long long i = (long long)row * d.nx + x;
                 f[k] = __ldg(frangi + i);
                 if (use_intensity) f[k] = f[k] * ((__ldg(raw + i) > intensity_thresh) ? 1.0f : 0.0f);   // labelling.py:550-552
-            } else if (w < nwin) {
-                f[k] = -INFINITY;
+                if (f[k] != f[k]) f[k] = -INFINITY;         // NaN > cut is false
             }
+            if (++xw == wpr) { xw = 0; ++row; }
         }
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            const int w = w0 + k;
-            const int row = w / wpr;
-            const bool inside = w < nwin && (w - row * wpr) * 32 + lane < d.nx;
-            const unsigned b = __ballot_sync(0xffffffffu, inside && !none && f[k] > cut);
-            if (lane == 0 && w < nwin) bits[w] = b;
+            const unsigned b = __ballot_sync(0xffffffffu, !none && f[k] > cut);
+            if (lane == 0 && w0 + k < nwin) bits[w0 + k] = b;
         }
     }
 }
@@ -154,7 +150,7 @@ pack_bits_kernel(const unsigned char* __restrict__ mask, Dims d, unsigned* __res
 //   [a+1, b+1] (linked by my voxel s-1, which sees the start diagonally: m1)
 //   6-conn: the first voxel of every overlap of two runs
 // ccl_border_kernel then makes the unions that cross a tile face with the same rules on global indices, and
-// ccl_flatten_tile_kernel resolves the tile roots first and everything else in one or two cached hops.
+// the two flatten kernels resolve the tile roots first and everything else in one cached hop.
 // History (512^3 frame of config #5, per labelling): voxel-wise init + merge + flatten with global atomics 2.8 ms;
 // this tile scheme with per-lane bit tests on byte masks 2.9 ms (the bit fiddling, 26 K warp instructions per tile);
 // word-wise as below: see DESIGN.md.
@@ -166,15 +162,6 @@ __device__ __forceinline__ int find_s(int* par, int x) {
         if (gp != p) par[x] = gp;      // path halving (ancestors stay ancestors: a stale store is harmless)
         x = p;
         p = gp;
-    }
-    return p;
-}
-
-__device__ __forceinline__ int find_s_ro(const int* par, int x) {
-    int p = *reinterpret_cast<const volatile int*>(par + x);
-    while (p != x && p >= 0) {
-        x = p;
-        p = *reinterpret_cast<const volatile int*>(par + x);
     }
     return p;
 }
@@ -220,11 +207,33 @@ ccl_tile_kernel(const unsigned* __restrict__ set_bits, unsigned char want, Dims 
         const int z = z0 + r / TY, y = y0 + r % TY;
         bits[r] = (y < d.ny && z < d.nz) ? set_word(set_bits, d, tg.tiles_x, z * d.ny + y, tx, want) : 0u;
     }
-    __syncthreads();
+    // whole tiles outside / inside the set are the common case (background around the tubes, tube-free blocks)
+    const bool row_full = threadIdx.x >= ROWS || bits[threadIdx.x] == 0xffffffffu;     // own word, written above
+    const bool row_empty = threadIdx.x >= ROWS || bits[threadIdx.x] == 0u;
+    const int all_full = __syncthreads_and(row_full), all_empty = __syncthreads_and(row_empty);
+    const int x = x0 + lane;
+    if (all_empty || all_full) {
+        // full: one component, its root the tile's first voxel (every row is valid, else its word would be 0)
+        const int origin = z0 * plane + y0 * d.nx + x0;
+        const bool outside = BORDER_OUTSIDE && all_full && (z0 == 0 || z0 + TZ >= d.nz || y0 == 0 || y0 + TY >= d.ny ||
+                                                             x0 == 0 || x0 + 32 >= d.nx);
+        const int val = all_empty ? NOT_IN_SET : (outside ? OUTSIDE : origin);
+#pragma unroll
+        for (int k = 0; k < ROWS / NW; ++k) {
+            const int r = warp + k * NW;
+            const int z = z0 + r / TY, y = y0 + r % TY;
+            if (y >= d.ny || z >= d.nz) continue;
+            if (lane == 0) root_bits[(long long)(z * d.ny + y) * tg.tiles_x + tx] = (all_full && !outside && r == 0) ? 1u : 0u;
+            if (x < d.nx) parent[z * plane + y * d.nx + x] = val;
+        }
+        if (all_full && !outside && area != nullptr && threadIdx.x == 0) area[origin] = ROWS * 32;
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < ROWS / NW; ++k) {
         const int r = warp + k * NW;
         const unsigned w = bits[r];
+        if (w == 0u) continue;                             // nobody reads par / cnt of a voxel outside the set
         int val = NOT_IN_SET;
         if ((w >> lane) & 1u) {
             const unsigned below_zero = ~w & lt;
@@ -326,7 +335,7 @@ ccl_tile_kernel(const unsigned* __restrict__ set_bits, unsigned char want, Dims 
         const unsigned w = bits[r];
         root[k] = NOT_IN_SET;
         if ((w >> lane) & 1u) {
-            root[k] = find_s_ro(par, r * 32 + lane);
+            root[k] = find_s(par, r * 32 + lane);         // halving: the chain of a tall local tree is walked once, not per row
             if (area != nullptr && root[k] >= 0 && !(lane > 0 && ((w >> (lane - 1)) & 1u))) {
                 const unsigned rest = ~(w >> lane);                  // first zero above me ends the run
                 atomicAdd(&cnt[root[k]], rest ? __ffs(rest) - 1 : 32 - lane);
@@ -334,7 +343,6 @@ ccl_tile_kernel(const unsigned* __restrict__ set_bits, unsigned char want, Dims 
         }
     }
     if (area != nullptr) __syncthreads();
-    const int x = x0 + lane;
 #pragma unroll
     for (int k = 0; k < ROWS / NW; ++k) {
         const int r = warp + k * NW;
@@ -457,50 +465,65 @@ ccl_border_kernel(const unsigned* __restrict__ set_bits, unsigned char want, Dim
     if (lane < n_q) unite(parent, q_[lane].x, q_[lane].y);
 }
 
-// parent[i] = root of i for every voxel of the set.  root_bits (one word per 32-voxel strip row, written by the tile
-// kernel) marks the voxels that were tile-local roots: only those can have been re-linked to another tile, so they
-// walk first; after the CTA barrier every other voxel reaches a root through its tile root in one or two cached hops.
-// Every store is a true root (no unions run concurrently), so concurrent walks of other CTAs stay valid.
-template <int TY, int TZ>
+// parent[i] = root of i for every voxel of the set, in two kernels.  root_bits (written by the tile kernel) marks the
+// voxels that were tile-local roots: only those can have been re-linked to another tile.  ccl_flatten_roots_kernel walks
+// all of them at once (one thread per word; inside the tile-structured kernel of the first version one walker per CTA
+// held its 255 siblings at the barrier for the 10-20 dependent L2 hops of a big component: 0.9 ms per pass);
+// ccl_flatten_voxels_kernel then gives every other voxel its tile root's root, one cached hop.
+// Every store is a true root (no unions run concurrently), so concurrent walks stay valid.
 __global__ void __launch_bounds__(THREADS)
-ccl_flatten_tile_kernel(Dims d, TileGrid tg, const unsigned* __restrict__ root_bits, int* __restrict__ parent,
-                        int* __restrict__ area) {
-    constexpr int ROWS = TY * TZ;
-    long long t = blockIdx.x;
-    const int tx = (int)(t % tg.tiles_x);
-    t /= tg.tiles_x;
-    const int ty = (int)(t % tg.tiles_y), tz = (int)(t / tg.tiles_y);
-    const int x0 = tx * 32, y0 = ty * TY, z0 = tz * TZ;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = x0 + lane;
-    const int plane = d.ny * d.nx;
-#pragma unroll
-    for (int k = 0; k < ROWS / (THREADS / 32); ++k) {
-        const int r = warp + k * (THREADS / 32);
-        const int z = z0 + r / TY, y = y0 + r % TY;
-        if (y >= d.ny || z >= d.nz) continue;
-        const unsigned rb = __ldg(root_bits + (long long)(z * d.ny + y) * tg.tiles_x + tx);
-        if (!((rb >> lane) & 1u)) continue;
-        const int i = z * plane + y * d.nx + x;
-        const int p = ld_parent(parent, i);
-        if (p >= 0 && p != i) {
-            const int f = find_root_ro(parent, p);
-            parent[i] = f;
-            // the size of a component is the sum over its tile-local pieces; area[i] of a non-root is final (nobody adds to it)
-            if (area != nullptr && f >= 0) atomicAdd(area + f, area[i]);
+ccl_flatten_roots_kernel(Dims d, const unsigned* __restrict__ root_bits, int* __restrict__ parent, int* __restrict__ area) {
+    const int wpr = (d.nx + 31) / 32;
+    const int nwords = d.nz * d.ny * wpr;
+    for (int wi = (int)(blockIdx.x * (long long)blockDim.x + threadIdx.x); wi < nwords; wi += (int)((long long)gridDim.x * blockDim.x)) {
+        unsigned rb = __ldg(root_bits + wi);
+        if (rb == 0u) continue;
+        const int row = wi / wpr;
+        const int i0 = row * d.nx + (wi - row * wpr) * 32;
+        while (rb) {
+            const int i = i0 + __ffs(rb) - 1;
+            rb &= rb - 1u;
+            const int p = ld_parent(parent, i);
+            if (p >= 0 && p != i) {
+                const int f = find_root_ro(parent, p);
+                parent[i] = f;
+                // the size of a component is the sum over its tile-local pieces; area[i] of a non-root is final
+                if (area != nullptr && f >= 0) atomicAdd(area + f, area[i]);
+            }
         }
     }
-    __syncthreads();
+}
+
+__global__ void __launch_bounds__(THREADS)
+ccl_flatten_voxels_kernel(Dims d, const unsigned* __restrict__ set_bits, unsigned char want, const unsigned* __restrict__ root_bits,
+                          int* __restrict__ parent) {
+    const int wpr = (d.nx + 31) / 32;
+    const int nwin = d.nz * d.ny * wpr;
+    const int lane = threadIdx.x & 31;
+    constexpr int U = 8;                                    // strips per warp and iteration
+    const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+    for (int w0 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * U; w0 < nwin; w0 += nwarps * U) {
+        int row = w0 / wpr, xw = w0 - row * wpr;
+        int idx[U], p[U];
 #pragma unroll
-    for (int k = 0; k < ROWS / (THREADS / 32); ++k) {
-        const int r = warp + k * (THREADS / 32);
-        const int z = z0 + r / TY, y = y0 + r % TY;
-        if (x >= d.nx || y >= d.ny || z >= d.nz) continue;
-        const int i = z * plane + y * d.nx + x;
-        const int p = ld_parent(parent, i);
-        if (p < 0 || p == i) continue;
-        const int q = ld_parent(parent, p);
-        if (q != p) parent[i] = find_root_ro(parent, q);       // q == p: p is a root and parent[i] is final already
+        for (int k = 0; k < U; ++k) {
+            p[k] = NOT_IN_SET;
+            if (w0 + k < nwin) {
+                // members that were not tile roots (those are final already)
+                const unsigned m = set_word(set_bits, d, wpr, row, xw, want) & ~__ldg(root_bits + w0 + k);
+                idx[k] = row * d.nx + xw * 32 + lane;
+                if ((m >> lane) & 1u) p[k] = ld_parent(parent, idx[k]);
+            }
+            if (++xw == wpr) { xw = 0; ++row; }
+        }
+        int q[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) q[k] = p[k] >= 0 ? ld_parent(parent, p[k]) : p[k];
+        // p is a former tile root (every ancestor is one), so q is final after ccl_flatten_roots_kernel; q == p: p is a root.
+        // (Checking q with one more load made every voxel of a big component read the same word: 0.9 ms per pass.)
+#pragma unroll
+        for (int k = 0; k < U; ++k)
+            if (p[k] >= 0 && q[k] != p[k]) parent[idx[k]] = q[k];
     }
 }
 
@@ -510,36 +533,53 @@ fill_holes_bits_kernel(Dims d, const int* __restrict__ parent, unsigned* __restr
     const int wpr = (d.nx + 31) / 32;
     const int nwin = d.nz * d.ny * wpr;
     const int lane = threadIdx.x & 31;
-    for (int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5); w < nwin;
-         w += (int)(((long long)gridDim.x * blockDim.x) >> 5)) {
-        const int row = w / wpr;
-        const int x = (w - row * wpr) * 32 + lane;
-        // flattened background labelling: root index (a hole), OUTSIDE, or NOT_IN_SET (foreground)
-        const bool hole = x < d.nx && parent[(long long)row * d.nx + x] >= 0;
-        const unsigned b = __ballot_sync(0xffffffffu, hole);
-        if (lane == 0 && b) bits[w] |= b;
+    constexpr int U = 8;
+    const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+    for (int w0 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * U; w0 < nwin; w0 += nwarps * U) {
+        int row = w0 / wpr, xw = w0 - row * wpr;
+        int p[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int x = xw * 32 + lane;
+            // flattened background labelling: root index (a hole), OUTSIDE, or NOT_IN_SET (foreground)
+            p[k] = (w0 + k < nwin && x < d.nx) ? parent[(long long)row * d.nx + x] : NOT_IN_SET;
+            if (++xw == wpr) { xw = 0; ++row; }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const unsigned b = __ballot_sync(0xffffffffu, p[k] >= 0);
+            if (lane == 0 && b) bits[w0 + k] |= b;
+        }
     }
 }
 
 // ---- size filter ---------------------------------------------------------------------------------
 // keep = component has at least min_area voxels (area[root] comes out of the labelling itself)
 __global__ void __launch_bounds__(THREADS)
-area_keep_bits_kernel(Dims d, const int* __restrict__ parent, const int* __restrict__ area, long long min_area,
-                      unsigned* __restrict__ keep_bits) {
+area_keep_bits_kernel(Dims d, const unsigned* __restrict__ set_bits, const int* __restrict__ parent, const int* __restrict__ area,
+                      long long min_area, unsigned* __restrict__ keep_bits) {
     const int wpr = (d.nx + 31) / 32;
     const int nwin = d.nz * d.ny * wpr;                     // <= voxels < 2^31
     const int lane = threadIdx.x & 31;
-    for (int w = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5); w < nwin;
-         w += (int)(((long long)gridDim.x * blockDim.x) >> 5)) {
-        const int row = w / wpr;
-        const int x = (w - row * wpr) * 32 + lane;
-        bool keep = false;
-        if (x < d.nx) {
-            const int r = parent[(long long)row * d.nx + x];
-            keep = r >= 0 && (long long)area[r] >= min_area;
+    constexpr int U = 8;
+    const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+    for (int w0 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * U; w0 < nwin; w0 += nwarps * U) {
+        int row = w0 / wpr, xw = w0 - row * wpr;
+        int r[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            r[k] = NOT_IN_SET;
+            if (w0 + k < nwin && ((__ldg(set_bits + w0 + k) >> lane) & 1u)) r[k] = parent[(long long)row * d.nx + xw * 32 + lane];
+            if (++xw == wpr) { xw = 0; ++row; }
         }
-        const unsigned bits = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) keep_bits[w] = bits;
+        int a[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) a[k] = r[k] >= 0 ? area[r[k]] : 0;
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const unsigned b = __ballot_sync(0xffffffffu, r[k] >= 0 && (long long)a[k] >= min_area);
+            if (lane == 0 && w0 + k < nwin) keep_bits[w0 + k] = b;
+        }
     }
 }
 
@@ -628,18 +668,26 @@ root_count_kernel(Dims d, const unsigned* __restrict__ root_bits, const int* __r
     if (lane == 0) block_counts[chunk] = c;
 }
 
-// single CTA: exclusive scan of block_counts in place; total -> *n_labels
+// single CTA: exclusive scan of block_counts in place; total -> *n_labels.  A thread owns 8 consecutive counts per round
+// (the one-count-per-thread form needed 128 rounds of four barriers for the 1.3 * 10^5 chunks of a 512^3 frame: 115 us)
 __global__ void __launch_bounds__(1024)
 block_scan_kernel(int* __restrict__ block_counts, long long nblocks, long long* __restrict__ n_labels) {
+    constexpr int V = 8;
     __shared__ int warp_tot[32];
     __shared__ int carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (long long base = 0; base < nblocks; base += 1024) {
-        const long long i = base + threadIdx.x;
-        const int v = i < nblocks ? block_counts[i] : 0;
-        int incl = v;
+    for (long long base = 0; base < nblocks; base += 1024 * V) {
+        const long long i0 = base + (long long)threadIdx.x * V;
+        int v[V];
+        int sum = 0;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            v[j] = i0 + j < nblocks ? block_counts[i0 + j] : 0;
+            sum += v[j];
+        }
+        int incl = sum;
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
@@ -656,10 +704,14 @@ block_scan_kernel(int* __restrict__ block_counts, long long nblocks, long long* 
         }
         __syncthreads();
         const int carry = carry_s;
-        const int before = (w ? warp_tot[w - 1] : 0) + carry;
-        if (i < nblocks) block_counts[i] = before + incl - v;
+        int run = (w ? warp_tot[w - 1] : 0) + carry + incl - sum;      // everything before this thread's first count
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if (i0 + j < nblocks) block_counts[i0 + j] = run;
+            run += v[j];
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry_s = before + incl;
+        if (threadIdx.x == 1023) carry_s = run;
         __syncthreads();
     }
     if (threadIdx.x == 0) *n_labels = (long long)carry_s;
@@ -733,7 +785,8 @@ int run_ccl_tiled(const unsigned* set_bits, unsigned char want, const Dims& d, b
     else ccl_tile_kernel<TY, TZ, true, true><<<g, THREADS, 0, st>>>(set_bits, want, d, tg, parent, root_bits, area);
     if (full_conn) ccl_border_kernel<TY, TZ, true><<<gs(words), THREADS, 0, st>>>(set_bits, want, d, parent);
     else ccl_border_kernel<TY, TZ, false><<<gs(words), THREADS, 0, st>>>(set_bits, want, d, parent);
-    ccl_flatten_tile_kernel<TY, TZ><<<g, THREADS, 0, st>>>(d, tg, root_bits, parent, area);
+    ccl_flatten_roots_kernel<<<gs(words), THREADS, 0, st>>>(d, root_bits, parent, area);
+    ccl_flatten_voxels_kernel<<<gs(d.total), THREADS, 0, st>>>(d, set_bits, want, root_bits, parent);
     return nb::check_launch("ccl");
 }
 
@@ -809,7 +862,7 @@ int nb200_label_frame(const float* frangi, const float* raw, int use_intensity, 
     // first labelling + size filter (labelling.py:489-501); the int32 output doubles as the size table
     rc = run_ccl(w.bits_a, 1, d, true, false, w.parent, w.bits_b, /*area=*/labels, st);
     if (rc) return rc;
-    area_keep_bits_kernel<<<gs(n), THREADS, 0, st>>>(d, w.parent, labels, min_area, w.bits_b);
+    area_keep_bits_kernel<<<gs(n), THREADS, 0, st>>>(d, w.bits_a, w.parent, labels, min_area, w.bits_b);
     // smoothing (labelling.py:503-505) and second labelling (:507)
     majority_bits_kernel<<<gs(w.words), THREADS, 0, st>>>(w.bits_b, d, w.bits_a);
     rc = run_ccl(w.bits_a, 1, d, true, false, w.parent, w.bits_b, nullptr, st);
