@@ -193,10 +193,9 @@ ccl_tile_kernel(const unsigned* __restrict__ set_bits, unsigned char want, Dims 
     __shared__ int par[ROWS * 32];
     __shared__ int cnt[ROWS * 32];
     __shared__ unsigned queue[NW][64];
-    long long t = blockIdx.x;
-    const int tx = (int)(t % tg.tiles_x);
-    t /= tg.tiles_x;
-    const int ty = (int)(t % tg.tiles_y), tz = (int)(t / tg.tiles_y);
+    __shared__ unsigned short heads[ROWS * 16];
+    __shared__ int n_heads;
+    const int tx = blockIdx.x, ty = blockIdx.y, tz = blockIdx.z;
     const int x0 = tx * 32, y0 = ty * TY, z0 = tz * TZ;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -327,7 +326,34 @@ ccl_tile_kernel(const unsigned* __restrict__ set_bits, unsigned char want, Dims 
         }
     }
     __syncthreads();
-    // ---- tile-local roots (and, for the size filter, voxels per local component, counted run by run) ----
+    // ---- tile-local roots.  Every inner node of the forest is the first voxel of an x-run (a "head": voxels start out
+    // pointing at their head and only roots are ever linked), so the heads are gathered, each walks its chain once and
+    // keeps the root, and every voxel is then two loads from its root.  (All 32 lanes of a row walking the same chain
+    // was a third of this kernel's instructions.)  Sizes for the size filter are counted run by run. ----
+    if (threadIdx.x == 0) n_heads = 0;
+    __syncthreads();
+    if (threadIdx.x < ROWS) {
+        const int r = threadIdx.x;
+        unsigned hm = bits[r] & ~(bits[r] << 1);
+        if (hm) {
+            int pos = atomicAdd(&n_heads, __popc(hm));
+            while (hm) {
+                heads[pos++] = (unsigned short)(r * 32 + __ffs(hm) - 1);
+                hm &= hm - 1u;
+            }
+        }
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h < n_heads; h += THREADS) {
+        const int idx = heads[h];
+        int x_ = idx, p_ = *reinterpret_cast<const volatile int*>(par + idx);
+        while (p_ != x_ && p_ >= 0) {                       // read-only walk; the only store is to the own entry
+            x_ = p_;
+            p_ = *reinterpret_cast<const volatile int*>(par + x_);
+        }
+        par[idx] = p_;                                      // own index for a root, OUTSIDE for a border-connected tree
+    }
+    __syncthreads();
     int root[ROWS / NW];
 #pragma unroll
     for (int k = 0; k < ROWS / NW; ++k) {
@@ -335,7 +361,8 @@ ccl_tile_kernel(const unsigned* __restrict__ set_bits, unsigned char want, Dims 
         const unsigned w = bits[r];
         root[k] = NOT_IN_SET;
         if ((w >> lane) & 1u) {
-            root[k] = find_s(par, r * 32 + lane);         // halving: the chain of a tall local tree is walked once, not per row
+            const int h = par[r * 32 + lane];               // a head above me (or, for a head, its root / OUTSIDE)
+            root[k] = h >= 0 ? par[h] : h;
             if (area != nullptr && root[k] >= 0 && !(lane > 0 && ((w >> (lane - 1)) & 1u))) {
                 const unsigned rest = ~(w >> lane);                  // first zero above me ends the run
                 atomicAdd(&cnt[root[k]], rest ? __ffs(rest) - 1 : 32 - lane);
@@ -775,9 +802,9 @@ int run_ccl_tiled(const unsigned* set_bits, unsigned char want, const Dims& d, b
     TileGrid tg;
     tg.tiles_x = (d.nx + 31) / 32;
     tg.tiles_y = (d.ny + TY - 1) / TY;
-    const long long tiles = (long long)tg.tiles_x * tg.tiles_y * ((d.nz + TZ - 1) / TZ);
-    NB_REQUIRE(tiles < 2147483647LL, NB200_ERR_UNSUPPORTED, "ccl: too many tiles");
-    const unsigned g = (unsigned)tiles;
+    const int tiles_z = (d.nz + TZ - 1) / TZ;
+    NB_REQUIRE(tg.tiles_y <= 65535 && tiles_z <= 65535, NB200_ERR_UNSUPPORTED, "ccl: more than 65535 tiles along Y or Z");
+    const dim3 g((unsigned)tg.tiles_x, (unsigned)tg.tiles_y, (unsigned)tiles_z);
     const long long words = (long long)d.nz * d.ny * tg.tiles_x;
     if (full_conn && !border_outside) ccl_tile_kernel<TY, TZ, true, false><<<g, THREADS, 0, st>>>(set_bits, want, d, tg, parent, root_bits, area);
     else if (!full_conn && border_outside) ccl_tile_kernel<TY, TZ, false, true><<<g, THREADS, 0, st>>>(set_bits, want, d, tg, parent, root_bits, area);
