@@ -6,15 +6,17 @@
 //   mask = uniform_filter(float32(mask), 3, mode="reflect") > 0.5   = (set voxels in the reflected 3^d window) >= 14 (5 in 2-D)
 //   labels = label(mask) : int32, ids 1..n in raster order of each component's first voxel (scipy.ndimage.label)
 //
-// Connected components: union-find over voxel indices in global memory.  X-runs are pre-linked
-// with warp ballots (every voxel starts pointing at the first voxel of its run inside a 32-wide
-// window), so only run heads ever take part in atomics; unions always hang the larger root under
-// the smaller one (atomicMin), so a component's root is its first voxel in raster order and
-// scipy's numbering is reproduced by ranking the roots.  Background components for fill-holes use
-// a virtual "outside" root (-2) that every border voxel links to.
+// Masks are packed (one 32-bit membership word per 32-voxel strip of a row) from the threshold to the last labelling.
+// Connected components: a CTA resolves a 32 x 8 x 8 tile (32 x 64 in 2-D) with a union-find in shared memory whose
+// unions are found on whole words (one union per overlap of two x-runs) and carried out 32 at a time; a second kernel
+// makes the unions that cross tile faces on global indices; tile roots walk to their root, every other voxel follows in
+// one hop.  Unions always hang the larger root under the smaller one (atomicMin), so a component's root is its first
+// voxel in raster order and scipy's numbering is reproduced by ranking the roots.  Background components for fill-holes
+// use a virtual "outside" root (-2) that every border voxel links to.  Component sizes for the size filter are summed
+// from the tiles' local counts while the tile roots are resolved.
 //
-// Integer / byte work: the bound is HBM traffic (frangi read + int32 labels write = 8 B/voxel
-// algorithmic; the parent array and the byte masks are honest extra traffic).
+// Integer / bit work: the algorithmic traffic is the frangi read + the int32 labels write = 8 B/voxel; the parent array
+// (written and re-read by each of the three labellings) is honest extra traffic, see DESIGN.md.
 #include "common.cuh"
 
 namespace {

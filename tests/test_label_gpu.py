@@ -105,6 +105,63 @@ def test_ccl_matches_scipy_label(shape, density, full):
     assert np.array_equal(got, ref.astype(np.int32))
 
 
+def _seam_cases():
+    """Structures aimed at the tile scheme (32 x 8 x 8 tiles in 3-D, 32 x 64 in 2-D): diagonals that cross tile corners,
+    blocks that contain whole tiles (the all-full fast path), thin sheets on tile faces."""
+    m = np.zeros((40, 50, 150), bool)
+    t = np.arange(40)
+    m[t, t, t] = True                                   # body diagonal through tile corners
+    m[t, t + 5, 149 - t] = True                         # the other way in x
+    m[t, 49 - t, 3 * t + 20] = False
+    m[t[:-1], 49 - t[:-1], 31 + (t[:-1] % 2)] = True    # zig-zag over the x = 31 | 32 strip boundary
+    m[8:32, 16:40, 32:128] = True                       # 3 x 3 x 3 whole tiles
+    m[16:24, 24:32, 64:96] = False                      # one whole tile of background inside
+    m[7, :, 40:100] = True                              # sheet just below a Z face
+    m[:, 7, 100:140] ^= True                            # sheet just below a Y face
+    m2 = np.zeros((130, 100), bool)
+    u = np.arange(100)
+    m2[u, u] = True
+    m2[u + 30, 99 - u] = True
+    m2[60:70, :] = True
+    m2[64, 20:80] = False
+    return [m, ~m, m2, ~m2]
+
+
+@pytest.mark.parametrize("case", range(4))
+@pytest.mark.parametrize("full", [True, False])
+def test_ccl_tile_seams(case, full):
+    import scipy.ndimage as ndi
+    mask = _seam_cases()[case]
+    ref, nref = ndi.label(mask, structure=np.ones((3,) * mask.ndim, bool) if full else None)
+    got, ngot = _ccl(mask, full)
+    assert ngot == nref
+    assert np.array_equal(got, ref.astype(np.int32))
+
+
+def test_label_frame_with_whole_tiles_of_foreground_and_cavities():
+    """Solid blocks larger than a tile (the all-full / all-empty tile fast paths), a cavity that is a whole background tile,
+    a cavity open to the frame border, a block flush with the frame border."""
+    from nellie_b200 import Label
+    from oracle import pipeline as P
+    rng = np.random.default_rng(5)
+    field = (0.2 * rng.random((48, 64, 160))).astype(np.float32)
+    field[4:44, 6:60, 10:150] = 0.9
+    field[16:24, 24:32, 64:96] = 0.1             # exactly one tile: enclosed
+    field[30:33, 40:44, 0:70] = 0.1              # channel open to x = 0
+    field[0:10, 0:12, 100:160] = 0.9             # flush with three faces of the frame
+    field[2:6, 3:7, 110:130] = 0.1               # enclosed cavity next to the border
+    field[rng.random(field.shape) < 0.002] = 1.0
+    dim_res = {"X": 0.2, "Y": 0.2, "Z": 0.25, "T": 1.0}
+    spec = P.FrameSpec(dim_res=dim_res, no_z=False)
+    stages = {}
+    ref = P.label_frame(field, spec, 0.5, stages=stages)
+    assert (stages["filled"] != (field > 0.5)).any()
+    lab = Label(_info(field.shape, dim_res, False), device="b200")
+    lab.num_t = 1
+    got = lab._run_frame_full_volume(0, field, field, None, 0.5)
+    assert np.array_equal(got, ref)
+
+
 def test_ccl_empty_and_full():
     got, n = _ccl(np.zeros((9, 10, 11), bool), True)
     assert n == 0 and not got.any()
