@@ -35,6 +35,21 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+
+def gate_threshold_f32(thresh, data_dtype) -> float:
+    """The float32 value T with ``float32(x) > T``  <=>  ``x > thresh`` as the reference evaluates it (labelling.py:419,
+    :550): numpy compares an integer frame, or any frame against a float64 *numpy* scalar, in float64 — exact — which for
+    operands representable in float32 (uint8 / uint16 / float32 frames) is the comparison against the largest float32
+    not above ``thresh``; a float32 frame against a Python float (the ``threshold=`` argument) or a float32 scalar (its
+    own Otsu threshold) is compared in float32, i.e. against ``thresh`` rounded to nearest."""
+    dt = np.dtype(data_dtype) if not isinstance(data_dtype, torch.dtype) else np.dtype(str(data_dtype).replace("torch.", ""))
+    exact = dt.kind in "iu" or (isinstance(thresh, np.floating) and thresh.dtype == np.float64 and dt == np.float32)
+    t32 = np.float32(thresh)
+    if exact and float(t32) > float(thresh):
+        t32 = np.nextafter(t32, np.float32(-np.inf), dtype=np.float32)
+    return float(t32)
+
+
 class LabelEngine:
     """Device buffers + kernel sequence for frames of one shape on one GPU."""
 
@@ -246,6 +261,8 @@ class Label:
         eng = self._engine_for(frame.shape)
         with torch.cuda.device(eng.device):
             gate = self._dev_f32(mask_frame) if (mask_frame is not None and mask_thresh is not None) else None
+            if gate is not None:
+                mask_thresh = gate_threshold_f32(mask_thresh, mask_frame.dtype)
             return eng.frangi_threshold(self._dev_f32(frame), gate, mask_thresh)
 
     def _compute_intensity_otsu_threshold(self, frame):
@@ -282,6 +299,8 @@ class Label:
         eng = self._engine_for(frangi_view.shape)
         with torch.cuda.device(eng.device):
             raw = self._dev_f32(original_view) if intensity_thresh is not None else None
+            if intensity_thresh is not None:
+                intensity_thresh = gate_threshold_f32(intensity_thresh, original_view.dtype)
             return eng.label(self._dev_f32(frangi_view), frangi_thresh, raw, intensity_thresh).cpu().numpy()
 
     def label_frame_device(self, frangi: torch.Tensor, raw: torch.Tensor = None):
@@ -293,6 +312,7 @@ class Label:
             if self.otsu_thresh_intensity or self.threshold is not None:
                 rawf = raw.to(torch.float32)
                 it = (eng.intensity_otsu(rawf) or 0) if self.otsu_thresh_intensity else self.threshold
+                it = gate_threshold_f32(it, raw.dtype)
             ft = eng.frangi_threshold(frangi, rawf, it)
             return eng.label(frangi, ft, rawf, it), ft
 

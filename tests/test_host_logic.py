@@ -296,3 +296,19 @@ def test_run_ladder_matches_the_reference_rules(monkeypatch):
         with pytest.raises(ValueError):
             st.run()
         assert calls == []
+
+
+def test_gate_threshold_reproduces_numpy_comparison_semantics():
+    """labelling.py:419, :550: ``frame > thresh`` is a float64 comparison for integer frames (and for float32 frames against
+    a float64 numpy scalar), a float32 comparison for float32 frames against a Python float; the device compares float32
+    values against ONE float32 number, which must therefore be chosen per case."""
+    from nellie_b200.labelling import gate_threshold_f32 as g
+    rng = np.random.default_rng(0)
+    x = np.arange(0, 65536, dtype=np.uint16)
+    for t in list(rng.uniform(0, 65535, 300)) + [999.99999999, 1000.0, 1000.00000001, 0.0, 65535.0, -3.5]:
+        assert np.array_equal(x > t, x.astype(np.float32) > np.float32(g(t, np.uint16))), t
+    xf = rng.uniform(0, 2, 100000).astype(np.float32)
+    for t in rng.uniform(0, 2, 300):
+        assert np.array_equal(xf > np.float64(t), xf > np.float32(g(np.float64(t), np.float32)))
+        assert np.array_equal(xf > float(t), xf > np.float32(g(float(t), np.float32)))
+        assert np.array_equal(xf > np.float32(t), xf > np.float32(g(np.float32(t), np.float32)))
