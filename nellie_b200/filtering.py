@@ -230,6 +230,9 @@ class Filter:
                 self.viewer.status = f"Preprocessing. Frame: {t + 1} of {self.num_t}."
 
         def after_store(t):
+            if single and self.frangi_memmap.ndim > len(frame_shape) and self.frangi_memmap.shape[0] > 1:
+                # filtering.py:1026-1027: ``frangi_memmap[:] = filtered_im[:]`` broadcasts the one frame over every T
+                self.frangi_memmap[1:] = self.frangi_memmap[0]
             if hasattr(self.frangi_memmap, "flush"):
                 self.frangi_memmap.flush()
 

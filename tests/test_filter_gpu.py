@@ -283,6 +283,24 @@ def test_filter_and_label_run_on_ome_tiff_files(tmp_path):
     assert np.array_equal(imio.read_tiff(info.im_path), frames), "raw stack was modified"
 
 
+def test_num_t_1_on_a_time_series_broadcasts_the_frame_like_the_reference(tmp_path):
+    """filtering.py:1026-1027: with ``num_t == 1`` the reference assigns ``frangi_memmap[:] = filtered_im[:]``, i.e. the
+    filtered first frame lands in EVERY timepoint of the output file."""
+    from nellie_b200 import Filter, imio
+    from nellie_b200.phantoms import tubular_phantom_np
+    dim_res = {"X": 0.1, "Y": 0.1, "Z": 0.2, "T": 1.0}
+    frames = np.stack([tubular_phantom_np((16, 40, 48), seed=900 + t, n_tubes=4) for t in range(3)])
+    info = imio.StackInfo.from_array(frames, "TZYX", dim_res, str(tmp_path), "p")
+    Filter(info, num_t=1, device="b200").run()
+    pre = imio.read_tiff(info.pipeline_paths["im_preprocessed"])
+    one = imio.StackInfo.from_array(frames[:1], "TZYX", dim_res, str(tmp_path / "one"), "p")
+    Filter(one, device="b200").run()
+    want = imio.read_tiff(one.pipeline_paths["im_preprocessed"])[0]
+    assert want.any()
+    for t in range(3):
+        assert np.array_equal(pre[t], want), t
+
+
 def test_2d_cuda_graph_replay_equals_eager_launches():
     """The 2-D per-frame sequence is replayed as one CUDA graph from the third call on; frames processed by replay
     must equal frames processed by eager launches, for changing inputs."""
