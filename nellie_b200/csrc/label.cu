@@ -523,91 +523,72 @@ ccl_flatten_roots_kernel(Dims d, const unsigned* __restrict__ root_bits, int* __
     }
 }
 
+// What each labelling is FOR is read off in the same pass that would otherwise only flatten the forest: after
+// ccl_flatten_roots_kernel a member is at most one hop from its root (a flagged tile root holds it, everybody else
+// reads it from the tile root it points at: every ancestor is a former tile root), so this kernel never stores a parent.
+//   HOLES   (background labelling): words |= members whose tree is not tied to OUTSIDE        (binary_fill_holes)
+//   KEEP    (first labelling):      keep words = members of components with >= min_area voxels (area[root] is complete)
+//   LABELS  (last labelling):       labels = number of the root (root_assign_kernel has run), 0 outside the set
+// (Checking a root with one more load made every voxel of a big component read the same word: 0.9 ms per pass.)
+enum { CONSUME_HOLES = 1, CONSUME_KEEP = 2, CONSUME_LABELS = 3 };
+
+template <int MODE>
 __global__ void __launch_bounds__(THREADS)
-ccl_flatten_voxels_kernel(Dims d, const unsigned* __restrict__ set_bits, unsigned char want, const unsigned* __restrict__ root_bits,
-                          int* __restrict__ parent) {
+ccl_consume_kernel(Dims d, const unsigned* set_bits, unsigned char want, const unsigned* root_bits,
+                   const int* __restrict__ parent, const int* area, long long min_area, unsigned* out_bits, int* labels) {
     const int wpr = (d.nx + 31) / 32;
     const int nwin = d.nz * d.ny * wpr;
     const int lane = threadIdx.x & 31;
-    constexpr int U = 8;                                    // strips per warp and iteration
+    constexpr int U = 8;                                    // strips per warp and iteration: loads in flight, one division
     const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
     for (int w0 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * U; w0 < nwin; w0 += nwarps * U) {
         int row = w0 / wpr, xw = w0 - row * wpr;
-        int idx[U], p[U];
+        int idx[U], root[U];
+        bool hop[U];
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-            p[k] = NOT_IN_SET;
+            root[k] = NOT_IN_SET;
+            hop[k] = false;
+            idx[k] = row * d.nx + xw * 32 + lane;
             if (w0 + k < nwin) {
-                // members that were not tile roots (those are final already)
-                const unsigned m = set_word(set_bits, d, wpr, row, xw, want) & ~__ldg(root_bits + w0 + k);
-                idx[k] = row * d.nx + xw * 32 + lane;
-                if ((m >> lane) & 1u) p[k] = ld_parent(parent, idx[k]);
+                const unsigned m = set_word(set_bits, d, wpr, row, xw, want);
+                if ((m >> lane) & 1u) {
+                    root[k] = __ldg(parent + idx[k]);
+                    hop[k] = root[k] >= 0 && !((root_bits[w0 + k] >> lane) & 1u);     // may alias out_bits (KEEP): own word, read first
+                }
             }
             if (++xw == wpr) { xw = 0; ++row; }
         }
-        int q[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k) q[k] = p[k] >= 0 ? ld_parent(parent, p[k]) : p[k];
-        // p is a former tile root (every ancestor is one), so q is final after ccl_flatten_roots_kernel; q == p: p is a root.
-        // (Checking q with one more load made every voxel of a big component read the same word: 0.9 ms per pass.)
 #pragma unroll
         for (int k = 0; k < U; ++k)
-            if (p[k] >= 0 && q[k] != p[k]) parent[idx[k]] = q[k];
-    }
-}
-
-// ---- fill holes: mask |= background voxels whose tree is not tied to OUTSIDE ----------------------
-__global__ void __launch_bounds__(THREADS)
-fill_holes_bits_kernel(Dims d, const int* __restrict__ parent, unsigned* __restrict__ bits) {
-    const int wpr = (d.nx + 31) / 32;
-    const int nwin = d.nz * d.ny * wpr;
-    const int lane = threadIdx.x & 31;
-    constexpr int U = 8;
-    const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
-    for (int w0 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * U; w0 < nwin; w0 += nwarps * U) {
-        int row = w0 / wpr, xw = w0 - row * wpr;
-        int p[U];
+            if (hop[k]) root[k] = __ldg(parent + root[k]);
+        if (MODE == CONSUME_HOLES) {
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const int x = xw * 32 + lane;
-            // flattened background labelling: root index (a hole), OUTSIDE, or NOT_IN_SET (foreground)
-            p[k] = (w0 + k < nwin && x < d.nx) ? parent[(long long)row * d.nx + x] : NOT_IN_SET;
-            if (++xw == wpr) { xw = 0; ++row; }
-        }
+            for (int k = 0; k < U; ++k) {
+                const unsigned b = __ballot_sync(0xffffffffu, root[k] >= 0);
+                if (lane == 0 && b) out_bits[w0 + k] |= b;
+            }
+        } else if (MODE == CONSUME_KEEP) {
+            int a[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const unsigned b = __ballot_sync(0xffffffffu, p[k] >= 0);
-            if (lane == 0 && b) bits[w0 + k] |= b;
-        }
-    }
-}
-
-// ---- size filter ---------------------------------------------------------------------------------
-// keep = component has at least min_area voxels (area[root] comes out of the labelling itself)
-__global__ void __launch_bounds__(THREADS)
-area_keep_bits_kernel(Dims d, const unsigned* __restrict__ set_bits, const int* __restrict__ parent, const int* __restrict__ area,
-                      long long min_area, unsigned* __restrict__ keep_bits) {
-    const int wpr = (d.nx + 31) / 32;
-    const int nwin = d.nz * d.ny * wpr;                     // <= voxels < 2^31
-    const int lane = threadIdx.x & 31;
-    constexpr int U = 8;
-    const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
-    for (int w0 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5) * U; w0 < nwin; w0 += nwarps * U) {
-        int row = w0 / wpr, xw = w0 - row * wpr;
-        int r[U];
+            for (int k = 0; k < U; ++k) a[k] = root[k] >= 0 ? area[root[k]] : 0;
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            r[k] = NOT_IN_SET;
-            if (w0 + k < nwin && ((__ldg(set_bits + w0 + k) >> lane) & 1u)) r[k] = parent[(long long)row * d.nx + xw * 32 + lane];
-            if (++xw == wpr) { xw = 0; ++row; }
-        }
-        int a[U];
+            for (int k = 0; k < U; ++k) {
+                const unsigned b = __ballot_sync(0xffffffffu, root[k] >= 0 && (long long)a[k] >= min_area);
+                if (lane == 0 && w0 + k < nwin) out_bits[w0 + k] = b;
+            }
+        } else {
+            int l[U];
 #pragma unroll
-        for (int k = 0; k < U; ++k) a[k] = r[k] >= 0 ? area[r[k]] : 0;
+            for (int k = 0; k < U; ++k) l[k] = (root[k] >= 0 && root[k] != idx[k]) ? labels[root[k]] : 0;
+            row = w0 / wpr;
+            xw = w0 - row * wpr;
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const unsigned b = __ballot_sync(0xffffffffu, r[k] >= 0 && (long long)a[k] >= min_area);
-            if (lane == 0 && w0 + k < nwin) keep_bits[w0 + k] = b;
+            for (int k = 0; k < U; ++k) {
+                // a root keeps the number root_assign_kernel gave it
+                if (w0 + k < nwin && xw * 32 + lane < d.nx && root[k] != idx[k]) labels[idx[k]] = l[k];
+                if (++xw == wpr) { xw = 0; ++row; }
+            }
         }
     }
 }
@@ -775,16 +756,6 @@ root_assign_kernel(Dims d, const unsigned* __restrict__ root_bits, const int* __
     }
 }
 
-__global__ void __launch_bounds__(THREADS)
-label_propagate_kernel(Dims d, const int* __restrict__ parent, int* __restrict__ labels) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < d.total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int r = parent[i];
-        if (r < 0) labels[i] = 0;
-        else if (r != (int)i) labels[i] = labels[r];
-    }
-}
-
 Dims make_dims(int nz, int ny, int nx) {
     Dims d;
     d.nz = nz; d.ny = ny; d.nx = nx;
@@ -796,8 +767,9 @@ Dims make_dims(int nz, int ny, int nx) {
 unsigned gs(long long n) { return nb::grid_for(n, THREADS, 8); }
 
 
-// parent[i] = root of i (first voxel of its component in raster order), OUTSIDE or NOT_IN_SET, for the set `want` of the
-// packed mask.  area (optional): on return area[r] = voxels of the component with root r (other entries are scratch).
+// The labelling of the set `want` of the packed mask, up to the point where every tile root (flagged in root_bits) holds
+// its root — the first voxel of its component in raster order, or OUTSIDE — and every other member points at a tile root;
+// ccl_consume_kernel reads the result off.  area (optional): on return area[r] = voxels of the component with root r.
 template <int TY, int TZ>
 int run_ccl_tiled(const unsigned* set_bits, unsigned char want, const Dims& d, bool full_conn, bool border_outside,
                   int* parent, unsigned* root_bits, int* area, cudaStream_t st) {
@@ -815,7 +787,6 @@ int run_ccl_tiled(const unsigned* set_bits, unsigned char want, const Dims& d, b
     if (full_conn) ccl_border_kernel<TY, TZ, true><<<gs(words), THREADS, 0, st>>>(set_bits, want, d, parent);
     else ccl_border_kernel<TY, TZ, false><<<gs(words), THREADS, 0, st>>>(set_bits, want, d, parent);
     ccl_flatten_roots_kernel<<<gs(words), THREADS, 0, st>>>(d, root_bits, parent, area);
-    ccl_flatten_voxels_kernel<<<gs(d.total), THREADS, 0, st>>>(d, set_bits, want, root_bits, parent);
     return nb::check_launch("ccl");
 }
 
@@ -854,7 +825,7 @@ int number_components(const Dims& d, const Workspace& w, int* labels, long long*
     root_count_kernel<<<ctas, THREADS, 0, st>>>(d, w.bits_b, w.parent, (int)w.words, w.block_counts);
     block_scan_kernel<<<1, 1024, 0, st>>>(w.block_counts, w.nblocks, n_labels);
     root_assign_kernel<<<ctas, THREADS, 0, st>>>(d, w.bits_b, w.parent, (int)w.words, w.block_counts, labels);
-    label_propagate_kernel<<<gs(d.total), THREADS, 0, st>>>(d, w.parent, labels);
+    ccl_consume_kernel<CONSUME_LABELS><<<gs(d.total), THREADS, 0, st>>>(d, w.bits_a, 1, w.bits_b, w.parent, nullptr, 0, nullptr, labels);
     return nb::check_launch("number_components");
 }
 
@@ -886,12 +857,13 @@ int nb200_label_frame(const float* frangi, const float* raw, int use_intensity, 
     if (fill_holes && nz > 1) {   // labelling.py:485-486 (3-D only)
         rc = run_ccl(w.bits_a, 0, d, /*full_conn=*/false, /*border_outside=*/true, w.parent, w.bits_b, nullptr, st);
         if (rc) return rc;
-        fill_holes_bits_kernel<<<gs(n), THREADS, 0, st>>>(d, w.parent, w.bits_a);
+        ccl_consume_kernel<CONSUME_HOLES><<<gs(n), THREADS, 0, st>>>(d, w.bits_a, 0, w.bits_b, w.parent, nullptr, 0, w.bits_a, nullptr);
     }
     // first labelling + size filter (labelling.py:489-501); the int32 output doubles as the size table
     rc = run_ccl(w.bits_a, 1, d, true, false, w.parent, w.bits_b, /*area=*/labels, st);
     if (rc) return rc;
-    area_keep_bits_kernel<<<gs(n), THREADS, 0, st>>>(d, w.bits_a, w.parent, labels, min_area, w.bits_b);
+    // keep words overwrite the root flags word by word (each word is read before it is written, by the same warp)
+    ccl_consume_kernel<CONSUME_KEEP><<<gs(n), THREADS, 0, st>>>(d, w.bits_a, 1, w.bits_b, w.parent, labels, min_area, w.bits_b, nullptr);
     // smoothing (labelling.py:503-505) and second labelling (:507)
     majority_bits_kernel<<<gs(w.words), THREADS, 0, st>>>(w.bits_b, d, w.bits_a);
     rc = run_ccl(w.bits_a, 1, d, true, false, w.parent, w.bits_b, nullptr, st);
