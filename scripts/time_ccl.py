@@ -1,5 +1,5 @@
-"""CUDA-event time of nb200_ccl_label alone on the foreground (26-conn) and the background (6-conn) of a 512^3 Frangi mask.
-NB200_CCL_STAGE = 1 tile | 2 + x seams | 3 + faces | 9 all (results are only valid for 9); NB200_CCL_LEGACY=1 the old kernels."""
+"""CUDA-event time of nb200_ccl_label alone (pack + tile + border + roots + numbering + labels) on a noisy 512^3 mask:
+the voxels above a cut (26-connectivity) and their complement (6-connectivity)."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -28,4 +28,4 @@ for name, m, full in (("fg26", fg, 1), ("bg6", bg, 0)):
     e1.record()
     torch.cuda.synchronize()
     out.append(f"{name}: {e0.elapsed_time(e1) / 5:.3f} ms ({int(cnt.item())} comps, frac {float(m.float().mean()):.3f})")
-print("stage", os.environ.get("NB200_CCL_STAGE", "9"), "legacy" if os.environ.get("NB200_CCL_LEGACY") else "tiled", " | ".join(out), flush=True)
+print(" | ".join(out), flush=True)

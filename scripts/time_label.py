@@ -1,4 +1,4 @@
-"""CUDA-event time of one Label frame (512^3 by default), tiled CCL against NB200_CCL_LEGACY=1 (run twice)."""
+"""CUDA-event time of one Label frame (512^3 by default): thresholds + nb200_label_frame through Label.label_frame_device."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from types import SimpleNamespace
@@ -23,5 +23,5 @@ for _ in range(10):
 e1.record()
 torch.cuda.synchronize()
 h = int(torch.hash_tensor(labels).item()) if hasattr(torch, "hash_tensor") else int(labels.to(torch.int64).sum().item())
-print("legacy" if os.environ.get("NB200_CCL_LEGACY") else "tiled", "label ms/frame", e0.elapsed_time(e1) / 10,
+print("label ms/frame", e0.elapsed_time(e1) / 10,
       "labels", int(labels.max()), "sum", int(labels.to(torch.int64).sum().item()), "hash", h, flush=True)
