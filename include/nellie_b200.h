@@ -142,6 +142,9 @@ int nb200_hist_bins(const float* vals, long long n, int transform, const double*
  * stage 0: HIST_MIN -> min, HIST_MAX -> max, Hessian stats -> max (every stats word reduces with MAX);
  * stage 1: HIST_COUNT and the 256 bins -> sum, Hessian stats -> max.  Other words of `state` are left alone. */
 int nb200_fold_records(const long long* gathered, int world, int stage, long long* state, void* stream);
+/* The same for `count` records per rank (rank r's records start at gathered + r * count * NB200_STATE_WORDS): a Z-sharded
+ * frame that runs a reduction point for all its sigmas at once (one all-gather instead of one per sigma). */
+int nb200_fold_records_n(const long long* gathered, int world, int count, int stage, long long* state, void* stream);
 /* gamma = min(triangle, otsu) (filtering.py:365-380) -> sp[GAMMA], sp[GAMMA_SQ] */
 int nb200_finalize_gamma(const long long* state, double* sp, void* stream);
 /* Frobenius threshold (filtering.py:407-444): consumes the histogram of frob samples and the

@@ -82,6 +82,7 @@ _SIGS = {
     "nb200_remove_connected_label_pixels": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_remove_edges": ([_p, C.c_int, C.c_int, C.c_int, C.c_int, _p], C.c_int),
     "nb200_fold_records": ([_p, C.c_int, C.c_int, _p, _p], C.c_int),
+    "nb200_fold_records_n": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_frangi_fast": ([_p, _p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, C.c_float, C.c_float, _p, _p, _p], C.c_int),
     "nb200_hessian_components": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, _p], C.c_int),
     "nb200_divisor_mode": ([C.c_float, C.POINTER(C.c_int), _p], C.c_int),

@@ -415,21 +415,26 @@ finalize_frob_kernel(const long long* state, const long long* hstats, double fix
 // records into the local one with the right operator per word (identical result on every rank).
 //   stage 0 (after hist_minmax / hessian stats): word MIN -> min, word MAX -> max, Hessian stats -> max
 //   stage 1 (after hist_bins):                    count + 256 bins -> sum,          Hessian stats -> max
-__global__ void fold_records_kernel(const long long* __restrict__ gathered, int world, int stage, long long* __restrict__ state) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= NB200_STATE_WORDS) return;
+// `count` records per rank (one per sigma when a Z-sharded frame reduces all its sigmas at one point): rank r's records
+// start at gathered + r * count * NB200_STATE_WORDS
+__global__ void fold_records_kernel(const long long* __restrict__ gathered, int world, int count, int stage,
+                                    long long* __restrict__ state) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count * NB200_STATE_WORDS) return;
+    const int i = j % NB200_STATE_WORDS;           // word inside its record
     const bool is_hs = i >= NB200_HIST_WORDS;
     int op = -1;                                   // 0 min, 1 max, 2 sum
     if (is_hs) op = 1;
     else if (stage == 0) op = i == NB200_HIST_MIN ? 0 : (i == NB200_HIST_MAX ? 1 : -1);
     else op = i >= NB200_HIST_COUNT ? 2 : -1;
     if (op < 0) return;
-    long long acc = gathered[i];
+    const long long stride = (long long)count * NB200_STATE_WORDS;
+    long long acc = gathered[j];
     for (int r = 1; r < world; ++r) {
-        const long long v = gathered[(long long)r * NB200_STATE_WORDS + i];
+        const long long v = gathered[(long long)r * stride + j];
         acc = op == 0 ? (v < acc ? v : acc) : (op == 1 ? (v > acc ? v : acc) : acc + v);
     }
-    state[i] = acc;
+    state[j] = acc;
 }
 
 __global__ void finalize_frob_resolve_kernel(const long long* hstats, double* sp) {
@@ -653,8 +658,15 @@ int nb200_finalize_frob_fast(const long long* state, const long long* hstats, do
 
 int nb200_fold_records(const long long* gathered, int world, int stage, long long* state, void* stream) {
     NB_REQUIRE(gathered && state && world >= 1 && (stage == 0 || stage == 1), NB200_ERR_ARG, "nb200_fold_records: bad argument");
-    fold_records_kernel<<<(NB200_STATE_WORDS + 255) / 256, 256, 0, nb::as_stream(stream)>>>(gathered, world, stage, state);
+    fold_records_kernel<<<(NB200_STATE_WORDS + 255) / 256, 256, 0, nb::as_stream(stream)>>>(gathered, world, 1, stage, state);
     return nb::check_launch("fold_records");
+}
+
+int nb200_fold_records_n(const long long* gathered, int world, int count, int stage, long long* state, void* stream) {
+    NB_REQUIRE(gathered && state && world >= 1 && count >= 1 && count <= 4096 && (stage == 0 || stage == 1), NB200_ERR_ARG,
+               "nb200_fold_records_n: bad argument");
+    fold_records_kernel<<<(count * NB200_STATE_WORDS + 255) / 256, 256, 0, nb::as_stream(stream)>>>(gathered, world, count, stage, state);
+    return nb::check_launch("fold_records_n");
 }
 
 int nb200_finalize_frob_resolve(const long long* hstats, double* sp, void* stream) {

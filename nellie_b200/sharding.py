@@ -131,26 +131,32 @@ class ZComm:
         the result is bit-identical on every rank (integers)."""
         if self.world == 1:
             return
-        if getattr(self, "_gath", None) is None or self._gath.device != state.device:
-            self._gath = torch.empty(self.world * state.numel(), dtype=state.dtype, device=state.device)
-        dist.all_gather_into_tensor(self._gath, state, group=self.group)
-        if state.is_cuda:
+        flat = state.reshape(-1)                      # one record, or one per sigma (batched reduction points): a view
+        count = flat.numel() // _cabi.STATE_WORDS
+        bufs = self.__dict__.setdefault("_gath_bufs", {})     # one per record count: captured graphs keep their pointers
+        key = (flat.numel(), str(flat.device))
+        if key not in bufs:
+            bufs[key] = torch.empty(self.world * flat.numel(), dtype=flat.dtype, device=flat.device)
+        self._gath = bufs[key]
+        dist.all_gather_into_tensor(self._gath, flat, group=self.group)
+        if flat.is_cuda:
             import ctypes as C
             lib = _cabi.load()
-            _cabi.check(lib.nb200_fold_records(C.c_void_p(self._gath.data_ptr()), self.world, int(stage),
-                                               C.c_void_p(state.data_ptr()),
-                                               C.c_void_p(torch.cuda.current_stream(state.device).cuda_stream)),
-                        "nb200_fold_records")
+            _cabi.check(lib.nb200_fold_records_n(C.c_void_p(self._gath.data_ptr()), self.world, count, int(stage),
+                                                 C.c_void_p(flat.data_ptr()),
+                                                 C.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)),
+                        "nb200_fold_records_n")
             return
         # host tensors (gloo tests of the plumbing): the same fold with torch ops
-        g = self._gath.view(self.world, state.numel())
+        g = self._gath.view(self.world, count, _cabi.STATE_WORDS)
+        rec = flat.view(count, _cabi.STATE_WORDS)
         hw = _cabi.HIST_WORDS
         if stage == _cabi.FOLD_MINMAX:
-            state[0] = g[:, 0].min()
-            state[1] = g[:, 1].max()
+            rec[:, 0] = g[:, :, 0].min(0).values
+            rec[:, 1] = g[:, :, 1].max(0).values
         else:
-            state[2:hw] = g[:, 2:hw].sum(0)
-        state[hw:] = g[:, hw:].max(0).values
+            rec[:, 2:hw] = g[:, :, 2:hw].sum(0)
+        rec[:, hw:] = g[:, :, hw:].max(0).values
 
     def gather_samples(self, samples: torch.Tensor, n: int):
         """All ranks' lattice samples concatenated (zero padded: consumers keep values > 0 only)."""
@@ -190,6 +196,8 @@ class ZShardedFilter:
         # for on 8 GPUs; capture them once and replay (NB200_NO_GRAPH=1 keeps eager launches)
         import os
         e.use_graph = self.world > 1 and not os.environ.get("NB200_NO_GRAPH")
+        # every reduction point once per frame for all sigmas instead of once per sigma (engine._run_sigmas_batched)
+        e.batch_sigmas = self.world > 1 and not os.environ.get("NB200_NO_BATCH")
         e.gather_samples = self._gather_samples
         self._pinned = None
 
