@@ -73,6 +73,21 @@ def _worker(rank, world, port, nz, halo, out_dir):
         assert int(rec[2]) == sum(3 * (r + 1) for r in contributing)
         assert bool((rec[3:hw] == sum(r + 1 for r in contributing)).all())
         assert int(rec[0]) == min(1000 + 10 * r for r in contributing), "stage 1 must not touch min / max"
+        # one reduction point for several sigmas at once: `count` records folded record by record
+        recs = torch.zeros((3, _cabi.STATE_WORDS), dtype=torch.int64)
+        for k in range(3):
+            recs[k, 0] = 100 * k + 10 * rank
+            recs[k, 1] = 100 * k + rank
+            recs[k, 2:hw] = (k + 1) * (rank + 1)
+            recs[k, hw:] = 1000 * k + rank
+        comm.fold_state(recs, _cabi.FOLD_MINMAX)
+        for k in range(3):
+            assert int(recs[k, 0]) == 100 * k and int(recs[k, 1]) == 100 * k + world - 1
+            assert bool((recs[k, 2:hw] == (k + 1) * (rank + 1)).all()), "stage 0 must not touch count / bins"
+            assert bool((recs[k, hw:] == 1000 * k + world - 1).all())
+        comm.fold_state(recs, _cabi.FOLD_BINS)
+        for k in range(3):
+            assert bool((recs[k, 2:hw] == (k + 1) * sum(r + 1 for r in range(world))).all())
         # lattice samples: ragged lengths, zero padded
         n = 4 + rank
         s = torch.arange(1, n + 1, dtype=torch.float32) + 100 * rank
