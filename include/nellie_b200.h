@@ -161,6 +161,13 @@ int nb200_finalize_max_abs(const long long* hstats, double* sp, void* stream);
  * float32 log10 (devmath.cuh np_log10f).  With log_domain = 0 it is the plain Otsu of labelling.py:457-465. */
 int nb200_finalize_label_threshold(const long long* state, int log_domain, double* out, void* stream);
 
+/* Otsu threshold of an INTEGER frame's positive samples, as numpy evaluates it (labelling.py:457-465 ->
+ * gpu_functions.py:23-50): np.histogram bins integer data with FLOAT64 edges and the threshold is a float64 bin centre.
+ * vals: the samples as float32 (exact for uint8 / uint16); state: after nb200_hist_reset + nb200_hist_minmax(TF_NONE).
+ * nb200_finalize_otsu_f64: out[0] = threshold, out[3] != 0 -> no samples, out[4] != 0 -> degenerate (NaN variance). */
+int nb200_hist_bins_f64(const float* vals, long long n, long long* state, void* stream);
+int nb200_finalize_otsu_f64(const long long* state, double* out, void* stream);
+
 /* ---- F4: Hessian statistics -------------------------------------------------------------
  * Finite-difference Hessian of numpy.gradient(numpy.gradient(.)) (filtering.py:446-562) at
  * every voxel of [zc0,zc1): reduces max|component| and max frob_sq into hstats and writes

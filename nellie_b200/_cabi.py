@@ -60,6 +60,8 @@ _SIGS = {
     "nb200_finalize_frob": ([_p, _p, C.c_double, C.c_double, _p, _p], C.c_int),
     "nb200_finalize_max_abs": ([_p, _p, _p], C.c_int),
     "nb200_finalize_label_threshold": ([_p, C.c_int, _p, _p], C.c_int),
+    "nb200_hist_bins_f64": ([_p, _ll, _p, _p], C.c_int),
+    "nb200_finalize_otsu_f64": ([_p, _p, _p], C.c_int),
     "nb200_hessian_stats": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p],
                             C.c_int),
     "nb200_hessian_stats_code": ([_p, C.POINTER(Vol), C.POINTER(C.c_float), C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p,

@@ -472,6 +472,124 @@ __global__ void __launch_bounds__(FIN_THREADS) finalize_label_kernel(const long 
 }
 
 // ------------------------------------------------------------------------------------------
+// Otsu threshold of an INTEGER frame (Label's intensity gate on uint8 / uint16 data, labelling.py:457-465):
+// numpy bins integer samples with float64 edges (np.histogram promotes the bin type of integer data to float64) and
+// otsu_threshold (gpu_functions.py:23-50) then works on float64 bin centres; the float32 kernels above would round the
+// edges and the centre.  The samples arrive as float32 (exact for |v| < 2^24), min / max come from the float32 keys of
+// nb200_hist_minmax; the edges, the binning and the centres here are float64.  Separate kernels on purpose: the float32
+// path (every fixture of the Filter) is not touched.
+// ------------------------------------------------------------------------------------------
+__device__ void build_edges_f64(double first, double last, double* edges /*NB+1*/, int tid, int nthreads) {
+    if (first == last) { first = first - 0.5; last = last + 0.5; }  // numpy _get_outer_edges
+    const double delta = last - first;
+    const double step = delta / (double)NB;
+    for (int i = tid; i <= NB; i += nthreads) {
+        double y = (double)i;
+        if (step == 0.0) { y = y / (double)NB; y = y * delta; }
+        else y = y * step;
+        y = y + first;
+        if (i == NB) y = last;
+        edges[i] = y;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hist_bins_f64_kernel(const float* __restrict__ vals, long long n, long long* __restrict__ state) {
+    __shared__ double edges[NB + 1];
+    __shared__ unsigned int local[NB];
+    if (state[NB200_HIST_COUNT] == 0) return;
+    float ff, fl;
+    outer_edges(state, ff, fl);
+    build_edges_f64((double)ff, (double)fl, edges, threadIdx.x, blockDim.x);
+    for (int i = threadIdx.x; i < NB; i += blockDim.x) local[i] = 0;
+    __syncthreads();
+    const double e_first = edges[0], e_last = edges[NB];
+    const double denom = e_last - e_first;      // numpy: _unsigned_subtract(last_edge, first_edge), exact for integers
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float raw = __ldg(vals + i);
+        if (!(raw > 0.0f)) continue;            // arr[arr > 0] (labelling.py:385-438)
+        const double t = (double)raw;
+        if (!(t >= e_first) || !(t <= e_last)) continue;
+        const double f = ((t - e_first) / denom) * (double)NB;
+        int b = (int)f;
+        if (b == NB) b = NB - 1;
+        if (t < edges[b]) --b;
+        else if (t >= edges[b + 1] && b != NB - 1) ++b;
+        atomicAdd(&local[b], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NB; i += blockDim.x)
+        if (local[i]) atomicAdd((unsigned long long*)&state[NB200_HIST_BINS + i], (unsigned long long)local[i]);
+}
+
+// out[0] = Otsu threshold (float64 bin centre), out[3] = 1 when there were no samples, out[4] = 1 when degenerate (NaN)
+__global__ void __launch_bounds__(FIN_THREADS) finalize_otsu_f64_kernel(const long long* state, double* out) {
+    __shared__ double edges[NB + 1], centers[NB], p[NB], pc[NB], w_lo[NB], s_lo[NB], w_hi[NB], s_hi[NB], val[NB];
+    __shared__ long long total_s;
+    const int t = threadIdx.x;
+    const bool have = state[NB200_HIST_COUNT] > 0;      // block-uniform
+    if (!have) {
+        if (t == 0) { out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; out[3] = 1.0; out[4] = 0.0; out[5] = 0.0; out[6] = 0.0; }
+        return;
+    }
+    float ff, fl;
+    outer_edges(state, ff, fl);
+    build_edges_f64((double)ff, (double)fl, edges, t, FIN_THREADS);
+    if (t == 0) {
+        long long total = 0;
+        for (int i = 0; i < NB; ++i) total += state[NB200_HIST_BINS + i];
+        total_s = total;
+    }
+    __syncthreads();
+    if (t < NB) {
+        centers[t] = (edges[t] + edges[t + 1]) / 2.0;
+        p[t] = (double)state[NB200_HIST_BINS + t] / (double)total_s;
+        pc[t] = p[t] * centers[t];
+    }
+    __syncthreads();
+    if (t == 0) {                    // reverse cumulative sums, in index order like np.cumsum on the reversed array
+        double aw = 0.0, as = 0.0;
+        for (int i = NB - 1; i >= 0; --i) {
+            aw = aw + p[i];
+            as = as + pc[i];
+            w_hi[i] = aw;
+            s_hi[i] = as;
+        }
+    } else if (t == 32) {
+        double aw = 0.0, as = 0.0;
+        for (int i = 0; i < NB; ++i) {
+            aw = aw + p[i];
+            as = as + pc[i];
+            w_lo[i] = aw;
+            s_lo[i] = as;
+        }
+    }
+    __syncthreads();
+    if (t < NB - 1) {
+        const double m_lo = s_lo[t] / w_lo[t];
+        const double m_hi = s_hi[t + 1] / w_hi[t + 1];
+        const double d = m_lo - m_hi;
+        val[t] = (w_lo[t] * w_hi[t + 1]) * (d * d);
+    }
+    __syncthreads();
+    if (t != 0) return;
+    double best = 0.0;
+    int arg = 0;
+    bool got = false, nan_hit = false;
+    for (int i = 0; i < NB - 1; ++i) {
+        const double var = val[i];
+        if (var != var) {  // np.argmax returns the first NaN
+            if (!nan_hit) { arg = i; nan_hit = true; }
+        } else if (!nan_hit && (!got || var > best)) {
+            best = var; arg = i; got = true;
+        }
+    }
+    out[0] = centers[arg]; out[1] = centers[arg]; out[2] = centers[arg];
+    out[3] = 0.0; out[4] = nan_hit ? 1.0 : 0.0; out[5] = centers[arg]; out[6] = centers[arg];
+}
+
+// ------------------------------------------------------------------------------------------
 // percentile by 3-pass radix select over the positive samples (F11, filtering.py:963)
 // scratch layout (int64): [0..2047] digit histogram, [2048] prefix, [2049] rank (k),
 //                         [2050] n_pos, [2051] found bits of s[k], [2052] bits of s[k+1]
@@ -679,6 +797,19 @@ int nb200_finalize_label_threshold(const long long* state, int log_domain, doubl
     NB_REQUIRE(state && out, NB200_ERR_ARG, "nb200_finalize_label_threshold: null argument");
     finalize_label_kernel<<<1, FIN_THREADS, 0, nb::as_stream(stream)>>>(state, log_domain, out);
     return nb::check_launch("finalize_label_threshold");
+}
+
+int nb200_hist_bins_f64(const float* vals, long long n, long long* state, void* stream) {
+    NB_REQUIRE(vals && state && n >= 0, NB200_ERR_ARG, "nb200_hist_bins_f64: bad argument");
+    if (n == 0) return NB200_OK;
+    hist_bins_f64_kernel<<<nb::grid_for(n, 256, 4), 256, 0, nb::as_stream(stream)>>>(vals, n, state);
+    return nb::check_launch("hist_bins_f64");
+}
+
+int nb200_finalize_otsu_f64(const long long* state, double* out, void* stream) {
+    NB_REQUIRE(state && out, NB200_ERR_ARG, "nb200_finalize_otsu_f64: null argument");
+    finalize_otsu_f64_kernel<<<1, FIN_THREADS, 0, nb::as_stream(stream)>>>(state, out);
+    return nb::check_launch("finalize_otsu_f64");
 }
 
 int nb200_percentile(const float* samples, long long n, double q_percent, long long* scratch, double* out,

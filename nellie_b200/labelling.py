@@ -82,13 +82,16 @@ class LabelEngine:
         self.launches += 1
         _cabi.check(getattr(self.lib, name)(*args), name)
 
-    def _hist_of(self, vals, n, transform):
+    def _hist_of(self, vals, n, transform, f64=False):
         st = _stream()
         self._call("nb200_hist_reset", _ptr(self.hist), st)
         self._call("nb200_hist_minmax", _ptr(vals), n, transform, None, _ptr(self.hist), st)
-        self._call("nb200_hist_bins", _ptr(vals), n, transform, None, _ptr(self.hist), st)
+        if f64:      # integer frame: numpy bins with float64 edges
+            self._call("nb200_hist_bins_f64", _ptr(vals), n, _ptr(self.hist), st)
+        else:
+            self._call("nb200_hist_bins", _ptr(vals), n, transform, None, _ptr(self.hist), st)
 
-    def _sample_hist(self, frame, transform, gate=None, gate_thresh=0.0):
+    def _sample_hist(self, frame, transform, gate=None, gate_thresh=0.0, f64=False):
         """labelling.py:385-438 (_sample_nonzero) + the histogram of the kept values. Returns count."""
         st = _stream()
         offsets = (0, self.step // 2) if self.step > 1 and self.step // 2 > 0 else (0,)
@@ -96,7 +99,7 @@ class LabelEngine:
             n_out = (self.n - off + self.step - 1) // self.step if off < self.n else 0
             self._call("nb200_strided_sample", _ptr(frame), self.n, off, self.step, _ptr(gate),
                        float(gate_thresh), _ptr(self.samples), st)
-            self._hist_of(self.samples, n_out, transform)
+            self._hist_of(self.samples, n_out, transform, f64)
             count = int(self.hist[2].item())
             if count > 0 or self.step == 1:
                 return count
@@ -106,7 +109,7 @@ class LabelEngine:
             tmp = torch.empty_like(full)
             self._call("nb200_strided_sample", _ptr(full), self.n, 0, 1, _ptr(gate), float(gate_thresh), _ptr(tmp), st)
             full = tmp
-        self._hist_of(full, self.n, transform)
+        self._hist_of(full, self.n, transform, f64)
         return int(self.hist[2].item())
 
     def frangi_threshold(self, frangi, gate=None, gate_thresh=None):
@@ -125,13 +128,18 @@ class LabelEngine:
         otsu = 10 ** np.float32(out[6])
         return float(min(triangle, otsu))
 
-    def intensity_otsu(self, raw_f32):
-        """labelling.py:457-465 (float32 arithmetic; exact for float32 inputs)."""
-        count = self._sample_hist(raw_f32, _cabi.TF_NONE)
+    def intensity_otsu(self, raw_f32, integer_frame=False):
+        """labelling.py:457-465.  float32 frames: float32 edges and centre, returned as np.float32 (what numpy yields);
+        integer frames (``integer_frame``; the values must be exact in float32: uint8 / uint16): float64 edges and centre,
+        returned as np.float64 — the scalar type decides how the gate compares (``gate_threshold_f32``)."""
+        count = self._sample_hist(raw_f32, _cabi.TF_NONE, f64=integer_frame)
         if count == 0:
             return None
+        if integer_frame:
+            self._call("nb200_finalize_otsu_f64", _ptr(self.hist), _ptr(self.thr), _stream())
+            return np.float64(self.thr.cpu().numpy()[0])
         self._call("nb200_finalize_label_threshold", _ptr(self.hist), 0, _ptr(self.thr), _stream())
-        return float(np.float32(self.thr.cpu().numpy()[0]))
+        return np.float32(self.thr.cpu().numpy()[0])
 
     def label(self, frangi, frangi_thresh, raw=None, intensity_thresh=None):
         """labelling.py:467-509 + :546-556. Returns the engine's int32 label tensor (device)."""
@@ -268,7 +276,8 @@ class Label:
     def _compute_intensity_otsu_threshold(self, frame):
         eng = self._engine_for(frame.shape)
         with torch.cuda.device(eng.device):
-            return eng.intensity_otsu(self._dev_f32(frame))
+            integer = (not frame.dtype.is_floating_point) if isinstance(frame, torch.Tensor) else np.dtype(frame.dtype).kind in "iu"
+            return eng.intensity_otsu(self._dev_f32(frame), integer_frame=integer)
 
     def _compute_frame_thresholds(self, original_view, frangi_view):
         intensity_thresh = None
@@ -311,7 +320,8 @@ class Label:
             rawf = None
             if self.otsu_thresh_intensity or self.threshold is not None:
                 rawf = raw.to(torch.float32)
-                it = (eng.intensity_otsu(rawf) or 0) if self.otsu_thresh_intensity else self.threshold
+                integer = not raw.dtype.is_floating_point
+                it = (eng.intensity_otsu(rawf, integer_frame=integer) or 0) if self.otsu_thresh_intensity else self.threshold
                 it = gate_threshold_f32(it, raw.dtype)
             ft = eng.frangi_threshold(frangi, rawf, it)
             return eng.label(frangi, ft, rawf, it), ft

@@ -186,6 +186,13 @@ def main():
     save_case("phantom3d_cfg3", c3, iso, False, sigmas=[1.0, 1.4, 1.8, 2.2, 2.6, 3.0])
     # (8) Filter._run_frame(t, mask=False) (filtering.py:910-933): no Frobenius gate
     save_case("phantom3d_nomask", tubular_phantom_np((20, 40, 48), seed=27, n_tubes=4), iso, False, run_mask=False)
+    # (9) / (10) Label's intensity gate (labelling.py:457-465, :511-556) with otsu_thresh_intensity=True: a uint16 frame
+    #     (numpy bins integer samples with float64 edges and compares raw > thresh in float64) and the same data as
+    #     float32 (float32 edges, float32 comparison)
+    u16 = np.clip(np.round(tubular_phantom_np((24, 56, 64), seed=28, n_tubes=6) * 37.0), 0, 65535).astype(np.uint16)
+    save_case("phantom3d_u16_otsu", u16, aniso, False, label_kwargs={"otsu_thresh_intensity": True})
+    save_case("phantom3d_f32_otsu", (u16.astype(np.float32) * np.float32(0.731)), aniso, False,
+              label_kwargs={"otsu_thresh_intensity": True})
     label_only_cases()
     network_cases()
 

@@ -26,8 +26,9 @@ def load_golden(name):
 def spec_from_meta(meta):
     from oracle.pipeline import FrameSpec
     fk = meta.get("filter_kwargs") or {}
+    lk = meta.get("label_kwargs") or {}
     return FrameSpec(dim_res=meta["dim_res"], no_z=meta["no_z"], sigmas=meta.get("explicit_sigmas"),
-                     run_mask=bool(meta.get("run_mask", True)), **fk)
+                     run_mask=bool(meta.get("run_mask", True)), **fk, **lk)
 
 
 @pytest.fixture(scope="session")

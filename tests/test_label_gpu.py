@@ -46,6 +46,30 @@ def test_label_on_reference_frangi(name):
     assert np.array_equal(labels, g["labels"])
 
 
+@pytest.mark.parametrize("name", ["phantom3d_u16_otsu", "phantom3d_f32_otsu"])
+def test_label_intensity_otsu_on_reference_frangi(name):
+    """Label(otsu_thresh_intensity=True) against the executed reference (labelling.py:457-465, :511-556): the gate
+    threshold of a uint16 frame is numpy's FLOAT64 bin centre (integer samples are binned with float64 edges) and the gate
+    compares in float64; a float32 frame gets float32 edges, centre and comparison.  Both must come out bit for bit, and
+    with them the gated Frangi threshold and the labels."""
+    import torch
+    from nellie_b200 import Label
+    g = load_golden(name)
+    lab = Label(_info(g["raw"].shape, g["meta"]["dim_res"], g["meta"]["no_z"]), device="b200", otsu_thresh_intensity=True)
+    lab.num_t = 1
+    it, ft = lab._compute_frame_thresholds(g["raw"], g["frangi"])
+    assert type(it) is (np.float64 if g["raw"].dtype.kind in "iu" else np.float32)
+    assert float(it) == float(g["intensity_thresh"]), (it, float(g["intensity_thresh"]))
+    assert ft == float(g["frangi_thresh"]), (ft, float(g["frangi_thresh"]))
+    labels = lab._run_frame_full_volume(0, g["raw"], g["frangi"], it, ft)
+    assert np.array_equal(labels, g["labels"])
+    # the device-resident path (Label.run's per-frame call) with the frame in its native dtype
+    raw_t = torch.from_numpy(g["raw"].astype(np.int32) if g["raw"].dtype == np.uint16 else g["raw"]).cuda()
+    dev_labels, ft2 = lab.label_frame_device(torch.from_numpy(g["frangi"]).cuda(), raw_t)
+    assert ft2 == float(g["frangi_thresh"])
+    assert np.array_equal(dev_labels.cpu().numpy(), g["labels"])
+
+
 def _tiny_info():
     return _info((5, 5), {"X": 1.0, "Y": 1.0, "Z": None, "T": 1.0}, True)
 

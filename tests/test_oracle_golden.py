@@ -37,6 +37,21 @@ def test_label_matches_reference(name):
     assert np.array_equal(labels, g["labels"])
 
 
+@pytest.mark.parametrize("name", ["phantom3d_u16_otsu", "phantom3d_f32_otsu"])
+def test_label_intensity_otsu_matches_reference(name):
+    """otsu_thresh_intensity=True (labelling.py:457-465, :511-556): the gate threshold is a float64 bin centre for the
+    uint16 frame and a float32 one for the float32 frame; the Frangi threshold is taken over the gated sample."""
+    g = load_golden(name)
+    spec = spec_from_meta(g["meta"])
+    assert spec.otsu_thresh_intensity
+    assert np.array_equal(P.finalize_mask(P.frangi_frame(g["raw"], spec), spec), g["frangi"])
+    it, ft = P.label_thresholds(g["raw"], g["frangi"], spec)
+    assert type(it) is (np.float64 if g["raw"].dtype.kind in "iu" else np.float32)
+    assert float(it) == float(g["intensity_thresh"]) and float(ft) == float(g["frangi_thresh"])
+    labels = P.label_frame(g["frangi"], spec, ft, raw=g["raw"], intensity_thresh=it)
+    assert np.array_equal(labels, g["labels"])
+
+
 @pytest.mark.parametrize("name", ["label3d", "label2d"])
 def test_label_only_cases(name):
     g = load_golden(name)
