@@ -333,6 +333,36 @@ int nb200_branch_labels(const unsigned char* pixel_class, int nz, int ny, int nx
                         long long* n_labels, void* stream);
 int nb200_remove_connected_label_pixels(const int* labels, int nz, int ny, int nx, int* out, void* stream);
 
+/* ---- Markers stage: nellie/segmentation/mocap_marking.py, full-volume branch --------------------------------
+ * Frames are (nz, ny, nx), nz = 1 for 2-D.  All kernels are exact (integer / comparison work, one float32 multiply), so the
+ * three outputs of Markers._run_frame_impl (mocap_marking.py:648-703) are bit-identical to the reference's.
+ * nb200_markers_mask_border: mask = labels > 0 (:657) and border = binary_dilation(mask, cross, 1 iteration) ^ mask (:440),
+ *   both uint8 0/1.
+ * nb200_markers_edt: scipy.ndimage.distance_transform_edt(mask).astype(float32) clamped with np.minimum(., clamp) (:444-447).
+ *   Exact squared distances by three windowed min-plus passes (X, Y, Z) with early exit; a voxel whose nearest background
+ *   voxel is further than `window` in some axis has a distance > window, so with window >= clamp the clamped result is
+ *   exact (NB200_ERR_ARG otherwise).  1 <= window <= 147 (squared distances are carried as uint16).  Voxels outside the
+ *   frame are NOT background (scipy semantics).  scratch: 2 * nz*ny*nx uint16.
+ * nb200_markers_log_response: resp = -(d0 + d1 [+ d2]) * sigma_sq, negatives set to 0 (:489-494); d0, d1, d2 are the
+ *   separable second-derivative Gaussians of scipy.ndimage.gaussian_laplace in axis order (built with nb200_gauss_axis /
+ *   nb200_gauss_yx and order-2 taps), d2 = NULL for 2-D; resp may alias d0.
+ * nb200_markers_peak_update: one scale of :496-505 — a voxel with mask != 0, distance > 0, resp equal to the maximum of its
+ *   3^d neighbourhood (clamped at the frame border) and resp > best gets best = resp, peak = 1.  best / peak are zeroed by
+ *   the caller before the first scale.
+ * nb200_markers_nms: :595-606 — marker = 1 where peak != 0, intensity > 0 and no peak inside the (2*radius+1)^d window
+ *   (clamped at the frame border) has a larger intensity; equal intensities keep each other, as the reference's
+ *   score == maximum_filter(score) does.  intensity: the raw frame as float32 (the cast of score_img[...] = intensity). */
+int nb200_markers_mask_border(const int* labels, int nz, int ny, int nx, unsigned char* mask, unsigned char* border,
+                              void* stream);
+int nb200_markers_edt(const unsigned char* mask, int nz, int ny, int nx, int window, float clamp,
+                      unsigned short* scratch, float* distance, void* stream);
+int nb200_markers_log_response(const float* d0, const float* d1, const float* d2, long long n, float sigma_sq,
+                               float* resp, void* stream);
+int nb200_markers_peak_update(const float* resp, const unsigned char* mask, const float* distance, int nz, int ny, int nx,
+                              float* best, unsigned char* peak, void* stream);
+int nb200_markers_nms(const unsigned char* peak, const float* intensity, int nz, int ny, int nx, int radius,
+                      unsigned char* marker, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,6 +82,11 @@ _SIGS = {
     "nb200_pixel_class": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_branch_labels": ([_p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p], C.c_int),
     "nb200_remove_connected_label_pixels": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
+    "nb200_markers_mask_border": ([_p, C.c_int, C.c_int, C.c_int, _p, _p, _p], C.c_int),
+    "nb200_markers_edt": ([_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _p, _p, _p], C.c_int),
+    "nb200_markers_log_response": ([_p, _p, _p, _ll, C.c_float, _p, _p], C.c_int),
+    "nb200_markers_peak_update": ([_p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p], C.c_int),
+    "nb200_markers_nms": ([_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_remove_edges": ([_p, C.c_int, C.c_int, C.c_int, C.c_int, _p], C.c_int),
     "nb200_fold_records": ([_p, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_fold_records_n": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),

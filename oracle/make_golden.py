@@ -154,6 +154,66 @@ def network_cases():
               f"junctions={int((pixel_class == 4).sum())} branches={int(branch.max())}")
 
 
+def _blob_case(shape, seed, n_blobs, r_max):
+    """Labelled solid balls / discs (radius 2..r_max) + an intensity frame with a few bright spots per object."""
+    rng = np.random.default_rng(seed)
+    grids = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    labels = np.zeros(shape, np.int32)
+    for k in range(1, n_blobs + 1):
+        c = [rng.uniform(0, s) for s in shape]
+        r = rng.uniform(2.0, r_max)
+        d2 = sum((g - ci) ** 2 for g, ci in zip(grids, c))
+        labels[d2 <= r * r] = k
+    raw = (rng.random(shape) * 40.0 + 200.0 * (labels > 0) * rng.random(shape)).astype(np.float32)
+    raw = np.round(raw).astype(np.uint16)          # integer intensities: ties between neighbouring peaks do occur
+    return raw, labels
+
+
+def marker_cases():
+    """Markers stage (mocap_marking.py:648-703 ``_run_frame_impl``, full-volume branch) executed by the unmodified
+    reference on the inputs of existing fixtures (raw + the reference's own labels / frangi) and on labelled blobs that
+    are thicker than 2 * max_radius_px (the distance clamp of :447 is active)."""
+    ref_shim.load()
+    from nellie.segmentation.mocap_marking import Markers
+
+    def run(name, raw, labels, dim_res, no_z, frangi=None, **kw):
+        info = ref_shim.im_info_for(raw.shape, dim_res, no_z)
+        m = Markers(info, num_t=1, device="cpu", **kw)
+        m.im_memmap = raw[None]
+        m.label_memmap = labels[None]
+        m.im_frangi_memmap = None if frangi is None else frangi[None]
+        m.shape = m.label_memmap.shape
+        m._set_default_sigmas()
+        marker, distance, border = m._run_frame_impl(0, low_memory=False)
+        meta = dict(dim_res=dim_res, no_z=no_z, kwargs=kw)
+        return dict(marker=np.asarray(marker, np.uint8), distance=np.asarray(distance, np.float32),
+                    border=np.asarray(border, np.uint8), sigmas=np.asarray(m.sigmas, np.float64),
+                    meta=np.asarray(json.dumps(meta)))
+
+    def from_fixture(name, parent, **kw):
+        z = np.load(os.path.join(GOLDEN_DIR, f"{parent}.npz"))
+        meta = json.loads(str(z["meta"]))
+        out = run(name, z["raw"], z["labels"], meta["dim_res"], meta["no_z"],
+                  frangi=z["frangi"] if kw.get("use_im") == "frangi" else None, **kw)
+        out["parent"] = np.asarray(parent)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **out)
+        print(f"{name}: markers={int(out['marker'].sum())} border={int(out['border'].sum())} "
+              f"max distance={float(out['distance'].max()):.4f} sigmas={out['sigmas'].round(3).tolist()}")
+
+    from_fixture("markers_sample_crop", "sample_crop")
+    from_fixture("markers_phantom3d_iso", "phantom3d_iso")
+    from_fixture("markers_phantom3d_aniso_frangi", "phantom3d_aniso", use_im="frangi", num_sigma=3)
+    from_fixture("markers_phantom2d", "phantom2d", peak_min_distance=3)
+    for name, shape, no_z, dim_res, kw in (
+            ("markers_blobs3d", (30, 56, 64), False, {"X": 0.2, "Y": 0.2, "Z": 0.3, "T": 1.0}, {}),
+            ("markers_blobs2d", (120, 140), True, {"X": 0.2, "Y": 0.2, "Z": None, "T": 1.0}, {"max_radius_um": 1.5})):
+        raw, labels = _blob_case(shape, 31 + len(shape), 12, 15.0 if not no_z else 22.0)
+        out = run(name, raw, labels, dim_res, no_z, **kw)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), raw=raw, labels=labels, **out)
+        print(f"{name}: markers={int(out['marker'].sum())} border={int(out['border'].sum())} "
+              f"max distance={float(out['distance'].max()):.4f} clamp={2.0 * (kw.get('max_radius_um', 1.0) / 0.2)}")
+
+
 def main():
     from nellie_b200.phantoms import tubular_phantom_np
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -195,6 +255,7 @@ def main():
               label_kwargs={"otsu_thresh_intensity": True})
     label_only_cases()
     network_cases()
+    marker_cases()
 
 
 if __name__ == "__main__":

@@ -566,3 +566,119 @@ def network_remove_connected(labels, no_z: bool):
     inner = np.zeros(labels.shape, bool)
     inner[tuple(slice(1, -1) for _ in labels.shape)] = True
     return np.where(amb & inner, 0, labels)
+
+
+# ---------------------------------------------------------------------------------------------
+# Markers stage: full-volume branch of nellie/segmentation/mocap_marking.py
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class MarkerSpec:
+    """Constructor knobs of ``Markers`` (mocap_marking.py:84-160) + the ``im_info`` attributes it reads."""
+
+    dim_res: dict
+    no_z: bool = False
+    min_radius_um: float = 0.20
+    max_radius_um: float = 1.0
+    use_im: str = "distance"
+    num_sigma: int = 5
+    peak_min_distance: int = 2
+
+    def x_res(self):
+        return self.dim_res.get("X") or 1.0
+
+    def z_ratio(self):
+        """mocap_marking.py:124-130."""
+        if self.no_z:
+            return 1.0
+        z_res = self.dim_res.get("Z") or self.x_res()
+        return float(z_res) / float(self.x_res())
+
+    def radii_px(self):
+        """mocap_marking.py:132-135: (min_radius_px, max_radius_px)."""
+        min_um = max(self.min_radius_um, float(self.x_res()))
+        return min_um / float(self.x_res()), self.max_radius_um / float(self.x_res())
+
+
+def marker_sigmas(spec: MarkerSpec):
+    """mocap_marking.py:340-378 (_set_default_sigmas)."""
+    min_px, max_px = spec.radii_px()
+    sigma_min = min_px / 2.0
+    sigma_max = max_px / 3.0
+    sigma_range = sigma_max - sigma_min
+    if sigma_range <= 0:
+        return [sigma_min]
+    step = max(0.2, sigma_range / max(spec.num_sigma, 1))
+    sigmas = list(np.arange(sigma_min, sigma_max, step))
+    return sigmas if sigmas else [sigma_min]
+
+
+def marker_sigma_vec(spec: MarkerSpec, sigma):
+    """mocap_marking.py:318-338 (_get_sigma_vec)."""
+    return (sigma, sigma) if spec.no_z else (sigma / spec.z_ratio(), sigma, sigma)
+
+
+def marker_distance(mask, spec: MarkerSpec):
+    """mocap_marking.py:419-450 (_distance_im): (distance float32 clamped to 2*max_radius_px, border shell bool)."""
+    mask = np.asarray(mask, dtype=bool)
+    border = ndi.binary_dilation(mask, iterations=1) ^ mask
+    distance = ndi.distance_transform_edt(mask)
+    distance = distance.astype(F32, copy=False)
+    np.minimum(distance, spec.radii_px()[1] * 2.0, out=distance)
+    return distance, border
+
+
+def marker_log_response(use_im, spec: MarkerSpec, sigma):
+    """mocap_marking.py:488-494: scale-normalised negated LoG of one sigma, negatives clamped, float32."""
+    sigma_val = float(sigma)
+    resp = -ndi.gaussian_laplace(use_im, marker_sigma_vec(spec, sigma_val))
+    resp = (resp * (sigma_val ** 2)).astype(F32, copy=False)
+    resp[resp < 0] = 0
+    return resp
+
+
+def marker_peaks(use_im, mask, distance, spec: MarkerSpec, sigmas=None):
+    """mocap_marking.py:452-512 (_local_max_peak, full-volume branch): bool peak mask (the reference returns
+    ``argwhere`` of it) and the best response per voxel."""
+    valid = np.asarray(mask, dtype=bool) & (distance > 0)
+    best = np.zeros_like(use_im, dtype=F32)
+    peak = np.zeros_like(use_im, dtype=bool)
+    for s in (marker_sigmas(spec) if sigmas is None else sigmas):
+        resp = marker_log_response(use_im, spec, s)
+        local_max = resp == ndi.maximum_filter(resp, size=3, mode="nearest")
+        local_max &= valid
+        better = local_max & (resp > best)
+        peak[better] = True
+        best[better] = resp[better]
+    return peak, best
+
+
+def marker_nms(peak, intensity, spec: MarkerSpec):
+    """mocap_marking.py:569-606 (_remove_close_peaks, full-volume branch): bool mask of the kept peaks."""
+    coords = np.argwhere(peak)
+    if coords.size == 0:
+        return np.zeros(peak.shape, bool)
+    score = np.zeros_like(intensity, dtype=F32)
+    score[tuple(coords.T)] = intensity[tuple(coords.T)]
+    size = 2 * int(spec.peak_min_distance) + 1
+    mx = ndi.maximum_filter(score, size=size, mode="nearest")
+    return (score == mx) & (score > 0)
+
+
+def marker_frame(intensity, labels, spec: MarkerSpec, frangi=None, sigmas=None):
+    """mocap_marking.py:648-703 (_run_frame_impl): (marker uint8, distance float32, border uint8)."""
+    intensity = np.asarray(intensity)
+    mask = (np.asarray(labels) > 0).astype(bool, copy=False)
+    if not mask.any():
+        return (np.zeros(intensity.shape, np.uint8), np.zeros(intensity.shape, F32), np.zeros(intensity.shape, np.uint8))
+    distance, border = marker_distance(mask, spec)
+    if spec.use_im == "distance":
+        base = distance
+    elif spec.use_im == "frangi":
+        if frangi is None:
+            raise RuntimeError("Frangi image requested for peak detection but not available.")
+        base = np.asarray(frangi)
+    else:
+        raise ValueError(f"Unknown use_im value: {spec.use_im}")
+    peak, _ = marker_peaks(base, mask, distance, spec, sigmas)
+    keep = marker_nms(peak, intensity, spec)
+    return keep.astype(np.uint8), distance, border.astype(np.uint8)
