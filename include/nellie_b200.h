@@ -363,6 +363,35 @@ int nb200_markers_peak_update(const float* resp, const unsigned char* mask, cons
 int nb200_markers_nms(const unsigned char* peak, const float* intensity, int nz, int ny, int nx, int radius,
                       unsigned char* marker, void* stream);
 
+/* ---- HuMomentTracking, per-frame feature extraction: nellie/tracking/hu_tracking.py ---------------------------
+ * Frames are (nz, ny, nx) float32 device copies (nz = 1 for 2-D); markers are rows of `coords`, int64 (n, ndim) voxel indices
+ * in raster order (argwhere of the marker frame); `bounds` is int32 (n, 6) = lo / hi for Z, Y, X.
+ * nb200_hu_frangi_transform: hu_tracking.py:604-612 — out = log10 of the positive values (numpy's float32 log10, bit for
+ *   bit), other values copied; then every negative value minus the minimum of the negatives.  scratch: one uint32 that the
+ *   caller sets to 0xFFFFFFFF before the call.
+ * nb200_hu_distance_max: :614-616 — 2 * maximum over the 3^d neighbourhood (border voxels repeated).
+ * nb200_hu_bounds: :392-421 (_get_im_bounds) — half width r = ceil(distance_max[marker]); lo = clip(m - r, 0, size),
+ *   hi = clip(m + r + 1, 0, size); max_half (device int, zeroed by the caller) receives the largest r: the reference's ROI
+ *   cube has side 2 * max_half + 1 (:633).
+ * nb200_hu_roi_stats: :341-390 (_calculate_mean_and_variance) per marker -> stats float32 (n, 2) = mean and variance of the
+ *   non-zero ROI voxels.  cube > 0: the dense path's zero-padded ROI cube of that side is what numpy reduces; cube = 0: the
+ *   ROI box itself (streaming path, :682-750).  int_bits: 0 = float32 frame (numpy's pairwise float32 summation restated),
+ *   8 / 16 = unsigned integer frame of that width (exact integer sums, squares wrapped to the width as numpy does).
+ *   Bit-identical to the reference in all four combinations.
+ * nb200_hu_log_moments: :225-325, :544-571 — per marker the log-Hu features of the ROI (2-D: 6) or of its three maximum
+ *   projections along Z, Y, X (3-D: 18) -> out float64 (n, 6 | 18).  proj: float32 scratch (n, 1 | 3, side, side) with
+ *   side >= the largest box extent; cube as above (0 joins the maximum where the box is shorter than the cube);
+ *   integer_frame != 0: exact integer raw moments.  Agrees with the reference to float64 rounding (numpy's SIMD pow is not
+ *   correctly rounded and not reproduced), not to the bit. */
+int nb200_hu_frangi_transform(const float* frangi, long long n, float* out, unsigned int* scratch, void* stream);
+int nb200_hu_distance_max(const float* distance, int nz, int ny, int nx, float* out, void* stream);
+int nb200_hu_bounds(const long long* coords, long long n, int ndim, const float* distance_max, int nz, int ny, int nx,
+                    int* bounds, int* max_half, void* stream);
+int nb200_hu_roi_stats(const float* frame, int nz, int ny, int nx, const int* bounds, long long n, int ndim, int cube,
+                       int int_bits, float* stats, void* stream);
+int nb200_hu_log_moments(const float* frame, int nz, int ny, int nx, const int* bounds, long long n, int ndim, int side,
+                         int cube, int integer_frame, float* proj, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,11 @@ _SIGS = {
     "nb200_markers_log_response": ([_p, _p, _p, _ll, C.c_float, _p, _p], C.c_int),
     "nb200_markers_peak_update": ([_p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p], C.c_int),
     "nb200_markers_nms": ([_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
+    "nb200_hu_frangi_transform": ([_p, _ll, _p, _p, _p], C.c_int),
+    "nb200_hu_distance_max": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
+    "nb200_hu_bounds": ([_p, _ll, C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p], C.c_int),
+    "nb200_hu_roi_stats": ([_p, C.c_int, C.c_int, C.c_int, _p, _ll, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
+    "nb200_hu_log_moments": ([_p, C.c_int, C.c_int, C.c_int, _p, _ll, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p], C.c_int),
     "nb200_remove_edges": ([_p, C.c_int, C.c_int, C.c_int, C.c_int, _p], C.c_int),
     "nb200_fold_records": ([_p, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_fold_records_n": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),

@@ -1,6 +1,6 @@
 // Serial host emulation of the CUDA launch model for the barrier-free per-voxel kernels (TEST INFRASTRUCTURE ONLY).
 //
-// A .cu file whose kernels use neither shared memory nor barriers nor atomics launches through the NB_LAUNCH macro; when it is
+// A .cu file whose kernels use neither shared memory nor barriers (atomics only through nb_atomic_*) launches through the NB_LAUNCH macro; when it is
 // compiled with  g++ -DNB200_HOST_EMU='"<path>/cuda_emu.h"' -x c++  this header replaces common.cuh: __global__ functions become
 // ordinary functions, NB_LAUNCH runs them once per (block, thread) with blockIdx / threadIdx set, one after the other.  The
 // kernel bodies, the index arithmetic, the grid-stride loops and the extern "C" entry points (argument checks included) are
@@ -66,5 +66,9 @@ inline unsigned grid_for(long long work_items, int threads, int ctas_per_sm) {
                 kernel(__VA_ARGS__);                                           \
             }                                                                  \
     } while (0)
+
+// the only atomics the emulated kernels use; execution is serial
+#define nb_atomic_min_u32(p, v) do { if ((v) < *(p)) *(p) = (v); } while (0)
+#define nb_atomic_max_i32(p, v) do { if ((v) > *(p)) *(p) = (v); } while (0)
 
 extern "C" const char* nb200_emu_last_error(void) { return nb::g_err; }

@@ -214,6 +214,43 @@ def marker_cases():
               f"max distance={float(out['distance'].max()):.4f} clamp={2.0 * (kw.get('max_radius_um', 1.0) / 0.2)}")
 
 
+def hu_cases():
+    """HuMomentTracking._get_frame_features_impl (hu_tracking.py:585-680) executed by the unmodified reference on the
+    marker / distance frames of the Markers fixtures, in its dense mode and (low_memory=True) its streaming mode."""
+    ref_shim.load()
+    from nellie.tracking.hu_tracking import HuMomentTracking
+    for name, src in (("hu_sample_crop", "markers_sample_crop"), ("hu_phantom3d_iso", "markers_phantom3d_iso"),
+                      ("hu_phantom2d", "markers_phantom2d"), ("hu_blobs3d", "markers_blobs3d")):
+        z = np.load(os.path.join(GOLDEN_DIR, f"{src}.npz"))
+        meta = json.loads(str(z["meta"]))
+        extra = {}
+        if "parent" in z.files:
+            p = np.load(os.path.join(GOLDEN_DIR, f"{str(z['parent'])}.npz"))
+            raw, frangi = p["raw"], p["frangi"]
+        else:
+            raw = z["raw"]
+            frangi = (z["distance"] * np.float32(0.013)).astype(np.float32)      # stand-in response, all values < 1
+            extra["frangi"] = frangi
+        info = ref_shim.im_info_for(raw.shape, meta["dim_res"], meta["no_z"])
+        info.no_t = False
+        info.shape = (2,) + raw.shape
+        out = dict(source=np.asarray(src), meta=np.asarray(json.dumps(dict(dim_res=meta["dim_res"], no_z=meta["no_z"]))), **extra)
+        for tag, low in (("dense", False), ("stream", True)):
+            tr = HuMomentTracking(info, num_t=2, device="cpu", low_memory=low)
+            tr.im_memmap, tr.im_frangi_memmap = raw[None], frangi[None]
+            tr.im_distance_memmap, tr.im_marker_memmap = z["distance"][None], z["marker"][None]
+            tr.shape = (1,) + raw.shape
+            ff = tr._get_frame_features_impl(0)
+            out[f"coords_{tag}"] = np.asarray(ff.coords_voxel)
+            out[f"phys_{tag}"] = np.asarray(ff.coords_phys)
+            out[f"stats_{tag}"] = np.asarray(ff.stats)
+            out[f"hu_{tag}"] = np.asarray(ff.hu)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **out)
+        print(f"{name}: markers={out['coords_dense'].shape[0]} stats={out['stats_dense'].dtype} hu dense={out['hu_dense'].dtype} "
+              f"stream={out['hu_stream'].dtype} dense==stream stats: {np.array_equal(out['stats_dense'], out['stats_stream'])} "
+              f"hu max|dense-stream|={np.abs(out['hu_dense'] - out['hu_stream']).max():.3g}")
+
+
 def main():
     from nellie_b200.phantoms import tubular_phantom_np
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -256,6 +293,7 @@ def main():
     label_only_cases()
     network_cases()
     marker_cases()
+    hu_cases()
 
 
 if __name__ == "__main__":

@@ -682,3 +682,153 @@ def marker_frame(intensity, labels, spec: MarkerSpec, frangi=None, sigmas=None):
     peak, _ = marker_peaks(base, mask, distance, spec, sigmas)
     keep = marker_nms(peak, intensity, spec)
     return keep.astype(np.uint8), distance, border.astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------
+# HuMomentTracking, per-frame feature extraction: nellie/tracking/hu_tracking.py:225-392, :585-750
+# ---------------------------------------------------------------------------------------------
+def hu_transform_frangi(frangi):
+    """hu_tracking.py:604-612: log10 of the positive response, then the negative values shifted so their minimum is 0."""
+    f = np.asarray(frangi).copy()
+    pos = f > 0
+    if np.any(pos):
+        f[pos] = np.log10(f[pos])
+    neg = f < 0
+    if np.any(neg):
+        f[neg] -= np.min(f[neg])
+    return f
+
+
+def hu_distance_max(distance):
+    """hu_tracking.py:614-616: 3^d maximum filter of the distance frame, doubled."""
+    d = np.asarray(distance).copy()
+    ndi.maximum_filter(d, size=3, output=d)
+    d *= 2
+    return d
+
+
+def hu_bounds(markers, distance_max, frame_shape):
+    """hu_tracking.py:392-421 (_get_im_bounds): per axis (low, high) as integer arrays (the reference keeps floats and
+    applies int() at the point of use)."""
+    radii = distance_max[tuple(markers.T)]
+    r = np.ceil(radii)
+    out = []
+    for a, size in enumerate(frame_shape):
+        out.append(np.clip(markers[:, a] - r, 0, size).astype(np.int64))
+        out.append(np.clip(markers[:, a] + (r + 1), 0, size).astype(np.int64))
+    return out
+
+
+def hu_mean_and_variance(images):
+    """hu_tracking.py:341-390 (_calculate_mean_and_variance) for (N, ...) ROI stacks."""
+    if images.size == 0:
+        return np.zeros((0, 2), F32)
+    feats = np.zeros((images.shape[0], 2), F32)
+    mask = images != 0
+    axis = tuple(range(1, images.ndim))
+    count = np.sum(mask, axis=axis)
+    safe = np.where(count == 0, 1, count)
+    s = np.sum(images * mask, axis=axis)
+    ss = np.sum((images * mask) ** 2, axis=axis)
+    mean = s / safe
+    var = (ss - (s ** 2) / safe) / safe
+    feats[:, 0] = np.where(count == 0, 0.0, mean)
+    feats[:, 1] = np.where(count == 0, 0.0, var)
+    return feats
+
+
+def hu_normalized_moments(images, real=np.float64):
+    """hu_tracking.py:225-268 (_calculate_normalized_moments), images (N, H, W).  ``real``: the float type of the
+    arithmetic (the reference: float64; tests pass np.longdouble to find the entries whose float64 value is rounding noise)."""
+    n, h, w = images.shape
+    ext = images[:, :, :, None, None]
+    if real is not np.float64:
+        ext = ext.astype(real)
+    x, y = np.meshgrid(np.arange(w), np.arange(h))
+    x = x[None, :, :, None, None]
+    y = y[None, :, :, None, None]
+    powers = np.arange(4)
+    px = powers[None, None, None, :, None]
+    py = powers[None, None, None, None, :]
+    M = np.sum(ext * (x ** px) * (y ** py), axis=(1, 2))
+    eps = real(1e-12)
+    x_bar = (M[:, 1, 0] / (M[:, 0, 0] + eps))[:, None, None, None, None]
+    y_bar = (M[:, 0, 1] / (M[:, 0, 0] + eps))[:, None, None, None, None]
+    mu = np.sum(ext * (x - x_bar) ** px * (y - y_bar) ** py, axis=(1, 2))
+    ipj = np.arange(4)[:, None] + np.arange(4)[None, :]
+    denom = (M[:, 0, 0][:, None, None] ** ((ipj[None, :, :] + 2) / real(2.0))) + eps
+    return mu / denom
+
+
+def hu_moments(eta):
+    """hu_tracking.py:270-312 (_calculate_hu_moments): first six Hu invariants."""
+    hu = np.zeros((eta.shape[0], 6), dtype=eta.dtype)
+    e20, e02, e11 = eta[:, 2, 0], eta[:, 0, 2], eta[:, 1, 1]
+    e30, e12, e21, e03 = eta[:, 3, 0], eta[:, 1, 2], eta[:, 2, 1], eta[:, 0, 3]
+    hu[:, 0] = e20 + e02
+    hu[:, 1] = (e20 - e02) ** 2 + 4 * e11 ** 2
+    hu[:, 2] = (e30 - 3 * e12) ** 2 + (3 * e21 - e03) ** 2
+    hu[:, 3] = (e30 + e12) ** 2 + (e21 + e03) ** 2
+    hu[:, 4] = ((e30 - 3 * e12) * (e30 + e12) * ((e30 + e12) ** 2 - 3 * (e21 + e03) ** 2) +
+                (3 * e21 - e03) * (e21 + e03) * (3 * (e30 + e12) ** 2 - (e21 + e03) ** 2))
+    hu[:, 5] = ((e20 - e02) * ((e30 + e12) ** 2 - (e21 + e03) ** 2) + 4 * e11 * (e30 + e12) * (e21 + e03))
+    return hu
+
+
+def hu_log(hu):
+    """hu_tracking.py:314-325 (_log_hu)."""
+    if hu.size == 0:
+        return hu
+    a = np.maximum(np.abs(hu), np.finfo(hu.dtype).tiny)
+    out = -np.sign(hu) * np.log10(a)
+    return np.where(np.isfinite(out), out, 0.0)
+
+
+def hu_of_subvolumes(sub, no_z, real=np.float64):
+    """hu_tracking.py:544-571 (_get_hu_moments): 6 invariants of a 2-D ROI, 18 of the three max projections of a 3-D ROI."""
+    if no_z:
+        return hu_moments(hu_normalized_moments(sub, real))
+    return np.concatenate([hu_moments(hu_normalized_moments(np.max(sub, axis=a), real)) for a in (1, 2, 3)], axis=1)
+
+
+def hu_frame_features(intensity, frangi, distance, marker, scaling, no_z, dense=True, real=np.float64):
+    """hu_tracking.py:585-680 (_get_frame_features_impl): (coords_voxel, coords_phys, stats (N, 4) float32, log-Hu (N, 6 | 18)).
+    dense=True: the batched zero-padded ROI cube of :641-657; dense=False: the per-ROI streaming path of :682-750."""
+    intensity = np.asarray(intensity)
+    fr = hu_transform_frangi(frangi)
+    dmax = hu_distance_max(distance)
+    marker_mask = np.asarray(marker) > 0
+    coords = np.argwhere(marker_mask)
+    dims = 2 if no_z else 3
+    if coords.size == 0:
+        return np.zeros((0, dims), int), np.zeros((0, dims), float), np.zeros((0, 0), F32), np.zeros((0, 0), F32)
+    phys = coords * np.asarray(scaling, dtype=float)
+    b = hu_bounds(coords, dmax, intensity.shape)
+    n = coords.shape[0]
+    R = int(np.ceil(np.max(dmax[marker_mask])).item()) * 2 + 1
+    hu_dim = 6 if no_z else 18
+    if dense:
+        def gather(frame):
+            sub = np.zeros((n,) + (R,) * dims, dtype=frame.dtype)
+            for i in range(n):
+                lo = [int(b[2 * a][i]) for a in range(dims)]
+                hi = [int(b[2 * a + 1][i]) for a in range(dims)]
+                if any(l >= h for l, h in zip(lo, hi)):
+                    continue
+                sub[(i,) + tuple(slice(0, h - l) for l, h in zip(lo, hi))] = frame[tuple(slice(l, h) for l, h in zip(lo, hi))]
+            return sub
+        isub, fsub = gather(intensity), gather(fr)
+        stats = np.concatenate([hu_mean_and_variance(isub), hu_mean_and_variance(fsub)], axis=1)
+        return coords.astype(int), phys, stats, hu_log(hu_of_subvolumes(isub, no_z, real))
+    stats = np.zeros((n, 4), F32)
+    log_hu = np.zeros((n, hu_dim), F32)
+    for i in range(n):
+        lo = [int(b[2 * a][i]) for a in range(dims)]
+        hi = [int(b[2 * a + 1][i]) for a in range(dims)]
+        if any(l >= h for l, h in zip(lo, hi)):
+            continue
+        sl = tuple(slice(l, h) for l, h in zip(lo, hi))
+        iroi, froi = intensity[sl][None], fr[sl][None]
+        stats[i] = np.concatenate((hu_mean_and_variance(iroi)[0], hu_mean_and_variance(froi)[0]), axis=0)
+        log_hu[i] = hu_log(hu_of_subvolumes(iroi, no_z, real)[0])
+    return coords.astype(int), phys, stats, log_hu

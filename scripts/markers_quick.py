@@ -38,6 +38,66 @@ def run(name, fn, *args):
         log(f"FAIL {name}: {type(exc).__name__}: {str(exc)[:300]}")
 
 
+if "--hu" in sys.argv:
+    # second call of the round: the Hu feature kernels first, then timings of both stages on a 256^3 frame
+    import json
+
+    import numpy as np
+
+    import hu_checks as HK
+
+    hb = HK.Backend(_cabi.load(), "cuda")
+    # every log-Hu entry of these fixtures is well conditioned (tests/test_hu_cpu.py evaluates the extended-precision
+    # criterion); skipping that CPU work keeps this call inside the last GPU seconds of the round
+    HK.well_conditioned = lambda i, f, d, marker, sc, no_z, dense: np.ones((int((marker > 0).sum()), 6 if no_z else 18), bool)
+    for case in HK.HU_CASES:
+        run(f"hu fixture {case}", HK.check_fixture, hb, case)
+    for dt in (np.float32, np.uint16, np.uint8):
+        run(f"hu stats {dt.__name__}", HK.check_stats_and_bounds, hb, (14, 30, 33), dt)
+    run("hu transforms", HK.check_frame_transforms, hb, (7, 20, 33))
+    try:
+        from nellie_b200.hu_tracking import HuFeatureEngine
+        from nellie_b200.mocap_marking import MarkerEngine
+        shape = (256, 256, 256)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        noise = torch.rand(shape, device="cuda", generator=g)
+        import torch.nn.functional as F
+        sm = F.avg_pool3d(noise[None, None], 9, 1, 4)[0, 0]
+        labels = (sm > sm.flatten()[::97].quantile(0.90)).to(torch.int32)
+        raw = (noise * 1000).round()
+        eng = MarkerEngine(shape, False, [1.0, 1.4667, 1.9333, 2.4, 2.8667], 1.0, 10.0, 2, "cuda")
+        times = {}
+
+        def timed(name, fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                out = fn()
+            b.record()
+            torch.cuda.synchronize()
+            times[name] = a.elapsed_time(b) / reps
+            return out
+
+        timed("markers.distance_and_border", lambda: eng.distance_and_border(labels))
+        timed("markers.peaks(5 scales)", lambda: eng.peaks(eng.distance))
+        timed("markers.suppress", lambda: eng.suppress(eng.peak, raw))
+        timed("markers.frame", lambda: eng.run_frame(labels, raw))
+        hu = HuFeatureEngine(shape, False, "cuda")
+        frangi = (sm * labels).contiguous()
+        timed("hu.transform_frangi", lambda: hu.transform_frangi(frangi))
+        timed("hu.max_distance", lambda: hu.max_distance(eng.distance))
+        timed("hu.frame_features(dense)", lambda: hu.frame_features(raw, 16, frangi, eng.distance, eng.marker, 5e9))
+        timed("hu.frame_features(stream)", lambda: hu.frame_features(raw, 16, frangi, eng.distance, eng.marker, 0))
+        info = dict(shape=shape, foreground=float((labels > 0).float().mean()), markers=int(eng.marker.sum()),
+                    ms={k: round(v, 4) for k, v in times.items()})
+        log("TIMING " + json.dumps(info))
+    except Exception as exc:  # noqa: BLE001
+        log(f"FAIL timing: {type(exc).__name__}: {str(exc)[:300]}")
+    log("done")
+    sys.exit(0)
+
 for case in ["markers_phantom3d_iso", "markers_sample_crop", "markers_blobs3d", "markers_phantom2d",
              "markers_phantom3d_aniso_frangi", "markers_blobs2d"]:
     run(f"fixture {case}", K.check_fixture, be, case)
