@@ -38,6 +38,45 @@ def run(name, fn, *args):
         log(f"FAIL {name}: {type(exc).__name__}: {str(exc)[:300]}")
 
 
+if "--mirror" in sys.argv:
+    # third call: the mirror classes themselves on the GPU (host arrays in, files out) and the blur kernels at the large
+    # radii / derivative taps the Markers scales use
+    import pathlib
+    import tempfile
+
+    import numpy as np
+    import scipy.ndimage as ndi
+
+    import hu_checks as HK
+    from nellie_b200 import Markers
+    from nellie_b200.hu_tracking import HuMomentFeatures
+
+    tmp = pathlib.Path(tempfile.mkdtemp())
+    run("mirror: reference's own marker tests", K.check_mirror_class_replays_reference_tests, Markers)
+    run("mirror: helpers + run() on files (+ T shards)", K.check_mirror_class_helpers_and_run_on_files, Markers, tmp / "a")
+    run("mirror: Markers.run() -> HuMomentFeatures on files", HK.check_markers_then_hu_on_files, Markers, HuMomentFeatures, tmp / "b")
+
+    def gauss_case(shape, sigma):
+        import ctypes as C
+        from nellie_b200.engine import gaussian_taps
+        from nellie_b200.engine2d import gaussian_taps_order2
+        rng = np.random.default_rng(int(sigma * 100) + shape[2])
+        x = (rng.random(shape, dtype=np.float32) * 20.0).astype(np.float32)
+        a = torch.from_numpy(x).cuda()
+        b = torch.empty_like(a)
+        v = _cabi.Vol.whole(*shape)
+        for order, (w, r) in ((0, gaussian_taps(sigma, 4.0)), (2, gaussian_taps_order2(sigma, 4.0))):
+            for axis in range(3):
+                _cabi.call("nb200_gauss_axis", C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.byref(v), axis,
+                           w.ctypes.data_as(C.POINTER(C.c_double)), r, be.stream())
+                ref = ndi.gaussian_filter1d(x, sigma, axis=axis, order=order, truncate=4.0, mode="reflect")
+                assert np.array_equal(b.cpu().numpy(), ref), (order, axis, r)
+
+    for sigma in (2.2, 2.87, 3.4, 4.4):
+        run(f"gauss_axis radius {int(4 * sigma + 0.5)} orders 0/2", gauss_case, (21, 45, 68), sigma)
+    log("done")
+    sys.exit(0)
+
 if "--hu" in sys.argv:
     # second call of the round: the Hu feature kernels first, then timings of both stages on a 256^3 frame
     import json
