@@ -392,6 +392,32 @@ int nb200_hu_roi_stats(const float* frame, int nz, int ny, int nx, const int* bo
 int nb200_hu_log_moments(const float* frame, int nz, int ny, int nx, const int* bounds, long long n, int ndim, int side,
                          int cube, int integer_frame, float* proj, double* out, void* stream);
 
+/* ---- Network stage, host steps of the reference moved to the device -------------------------------------------
+ * Frames are int32 (nz, ny, nx), nz = 1 for 2-D, fewer than 2^32 voxels; object ids 1..max_label.
+ * nb200_network_add_missing: networking.py:315-392 — an object whose label does not occur in `skel` gets skel[p] = label at
+ *   the voxel p of its largest Frangi response (first voxel in raster order among equal values; scipy's own choice among
+ *   exactly equal values follows an unstable sort).  key: uint64[max_label + 1], in_skel: uint8[max_label + 1], both zeroed
+ *   by the caller.
+ * nb200_network_skeleton_labels: :835 — out = skel > 0 ? labels : 0.
+ * nb200_network_object_boxes: scipy.ndimage.find_objects — boxes int32 (max_label + 1, 6) = min z, y, x (caller fills
+ *   INT_MAX) and max z, y, x (caller fills -1); seeded[lab] (uint8, zeroed) = 1 when the object holds a voxel with branch > 0.
+ * nb200_network_relabel: :485-577 (_relabel_objects) — for every row of `crops` (int64 (m, 8) = label, z0, y0, x0, extents
+ *   ez, ey, ex, offset of the crop in crop space; ascending offsets) the feature transform of the object's seeds
+ *   (label == row label and branch > 0) over its bounding box, exactly as scipy.ndimage.distance_transform_edt(~seeds,
+ *   sampling, return_indices=True) computes it (tie-breaking included), then out[v] = branch[nearest seed of v] for the
+ *   object's voxels; other voxels of `out` (uint32, zeroed by the caller) are left alone.  crop_voxels = sum of the box
+ *   volumes; line_starts int64 (3, m) = per axis the exclusive prefix sum of the number of crop lines along that axis,
+ *   n_lines (HOST, 3) their totals; sampling (HOST double[3]) = voxel size along Z, Y, X; ft_a, ft_b: int32 (3, crop_voxels),
+ *   stack: int32 (crop_voxels). */
+int nb200_network_add_missing(const int* labels, const float* frangi, int* skel, int nz, int ny, int nx, int max_label,
+                              unsigned long long* key, unsigned char* in_skel, void* stream);
+int nb200_network_skeleton_labels(const int* skel, const int* labels, long long n, int* out, void* stream);
+int nb200_network_object_boxes(const int* labels, const int* branch, int nz, int ny, int nx, int max_label, int* boxes,
+                               unsigned char* seeded, void* stream);
+int nb200_network_relabel(const int* labels, const int* branch, int nz, int ny, int nx, const long long* crops, long long m,
+                          long long crop_voxels, const long long* line_starts, const long long* n_lines,
+                          const double* sampling, int* ft_a, int* ft_b, int* stack, unsigned int* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

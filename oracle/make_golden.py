@@ -251,6 +251,62 @@ def hu_cases():
               f"hu max|dense-stream|={np.abs(out['hu_dense'] - out['hu_stream']).max():.3g}")
 
 
+def standin_skeleton(mask):
+    """Deterministic thin subset of a mask standing in for skimage.morphology.skeletonize (scikit-image is not in this
+    image): the ridge of the Euclidean distance transform.  Every step AFTER the thinning is what the fixtures pin."""
+    import scipy.ndimage as ndi
+    mask = np.asarray(mask, bool)
+    d = ndi.distance_transform_edt(mask)
+    return (d == ndi.maximum_filter(d, size=3)) & mask
+
+
+def standin_skeleton_half(mask):
+    """The same ridge with nothing in the lower-X half of the frame: objects that live there end up without a skeleton
+    voxel, which is the case networking.py:315-392 (_add_missing_skeleton_labels) exists for."""
+    sk = standin_skeleton(mask)
+    sk[..., : mask.shape[-1] // 2] = False
+    return sk
+
+
+def network_frame_cases():
+    """Network._run_frame_backend (networking.py:825-851) executed by the unmodified reference on the labels / Frangi frames
+    of existing fixtures, with ``skimage.morphology.skeletonize`` replaced by ``standin_skeleton`` (the one substitution;
+    scikit-image is absent here), plus the two host steps on their own (_add_missing_skeleton_labels, _relabel_objects)."""
+    import sys
+    ref_shim.load()
+    sys.modules["skimage"].morphology = sys.modules["skimage.morphology"]
+    from nellie.segmentation import networking as ref_net
+    ref_net.morph = sys.modules["skimage.morphology"]
+    for name, parent in (("network_frame_sample_crop", "sample_crop"), ("network_frame_phantom3d_aniso", "phantom3d_aniso"),
+                         ("network_frame_phantom2d", "phantom2d"), ("network_frame_cfg3", "phantom3d_cfg3"),
+                         ("network_frame_cfg3_half", "phantom3d_cfg3"), ("network_frame_phantom2d_half", "phantom2d")):
+        sys.modules["skimage.morphology"].skeletonize = standin_skeleton_half if name.endswith("_half") else standin_skeleton
+        z = np.load(os.path.join(GOLDEN_DIR, f"{parent}.npz"))
+        meta = json.loads(str(z["meta"]))
+        from oracle.pipeline import tie_free
+        labels, frangi = z["labels"], tie_free(z["frangi"])       # unique maxima per object: see tie_free
+        dim_res = dict(meta["dim_res"])
+        if meta["no_z"]:
+            dim_res["Z"] = dim_res.get("Z") or 1.0
+        info = ref_shim.im_info_for(labels.shape, dim_res, meta["no_z"])
+        net = ref_net.Network(info, num_t=1, device="cpu")
+        net.label_memmap, net.im_frangi_memmap = labels[None], frangi[None]
+        net.shape = net.label_memmap.shape
+        skel0 = net._skeletonize(labels)
+        cleaned = net._remove_connected_label_pixels(skel0, force_cpu=True)
+        added = net._add_missing_skeleton_labels(np.array(cleaned, copy=True), labels, frangi)
+        branch, pixel_class, relabelled = net._run_frame_backend(0)
+        out = dict(parent=np.asarray(parent), skeleton=np.asarray(skel0 > 0), cleaned=np.asarray(cleaned, np.int32),
+                   added=np.asarray(added, np.int32), branch=np.asarray(branch, np.int32),
+                   pixel_class=np.asarray(pixel_class, np.uint8), relabelled=np.asarray(relabelled, np.uint32),
+                   scaling=np.asarray(net.scaling, np.float64),
+                   meta=np.asarray(json.dumps(dict(dim_res=dim_res, no_z=meta["no_z"]))))
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), **out)
+        n_missing = int(np.setdiff1d(np.unique(labels), np.unique(cleaned)).size)
+        print(f"{name}: objects={int(labels.max())} skeleton voxels={int((skel0 > 0).sum())} objects without skeleton={n_missing} "
+              f"branches={int(branch.max())} junction voxels={int((pixel_class == 4).sum())} relabelled voxels={int((relabelled > 0).sum())}")
+
+
 def main():
     from nellie_b200.phantoms import tubular_phantom_np
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -294,6 +350,7 @@ def main():
     network_cases()
     marker_cases()
     hu_cases()
+    network_frame_cases()
 
 
 if __name__ == "__main__":

@@ -832,3 +832,72 @@ def hu_frame_features(intensity, frangi, distance, marker, scaling, no_z, dense=
         stats[i] = np.concatenate((hu_mean_and_variance(iroi)[0], hu_mean_and_variance(froi)[0]), axis=0)
         log_hu[i] = hu_log(hu_of_subvolumes(iroi, no_z, real)[0])
     return coords.astype(int), phys, stats, log_hu
+
+
+# ---------------------------------------------------------------------------------------------
+# Network stage, host steps: networking.py:315-392, :485-577, :825-851
+# ---------------------------------------------------------------------------------------------
+def network_add_missing(skel, labels, frangi):
+    """networking.py:315-392 (_add_missing_skeleton_labels): objects without a skeleton voxel get one at the position of
+    their largest Frangi response."""
+    skel = np.array(skel, copy=True)
+    labels = np.asarray(labels)
+    missing = np.setdiff1d(np.unique(labels), np.unique(skel))
+    missing = missing[missing != 0]
+    if missing.size == 0:
+        return skel
+    positions = ndi.maximum_position(np.asarray(frangi), labels=labels, index=missing)
+    for lab, pos in zip(missing, positions):
+        skel[tuple(int(p) for p in pos)] = lab
+    return skel
+
+
+def network_relabel_objects(branch, labels, scaling):
+    """networking.py:485-577 (_relabel_objects): per object, every voxel takes the branch label of the nearest seed."""
+    labels = np.asarray(labels).astype(np.int32, copy=False)
+    branch = np.asarray(branch).astype(np.int32, copy=False)
+    out = np.zeros_like(labels, dtype=np.uint32)
+    max_label = int(labels.max())
+    if max_label == 0:
+        return out
+    slices = ndi.find_objects(labels)
+    for lab in range(1, max_label + 1):
+        sl = slices[lab - 1]
+        if sl is None:
+            continue
+        obj = labels[sl] == lab
+        sub_branch = branch[sl]
+        seeds = (sub_branch > 0) & obj
+        if not seeds.any():
+            continue
+        idx = ndi.distance_transform_edt(np.logical_not(seeds), sampling=scaling, return_distances=False,
+                                         return_indices=True)
+        nearest = sub_branch[tuple(idx)]
+        nearest[~obj] = 0
+        sub = out[sl]
+        sub[obj] = nearest[obj].astype(np.uint32, copy=False)
+        out[sl] = sub
+    return out
+
+
+def network_frame(labels, frangi, skeleton_mask, scaling, no_z):
+    """networking.py:825-851 (_run_frame_backend) given the skeleton mask the host thinning produced (:394-410:
+    skel_frame = labels * skeletonize(labels > 0)): (branch_skel_labels, pixel_class, branch_labels)."""
+    labels = np.asarray(labels)
+    skel = labels * np.asarray(skeleton_mask).astype(bool)
+    skel = network_remove_connected(skel, no_z)
+    skel = network_add_missing(skel, labels, frangi)
+    skel_pre = (skel > 0) * labels
+    pixel_class = network_pixel_class(skel_pre, no_z)
+    branch = network_branch_labels(pixel_class, no_z)
+    return branch, pixel_class, network_relabel_objects(branch, labels, scaling)
+
+
+def tie_free(frangi):
+    """Test inputs only: the phantoms' Frangi frames hold exactly equal maxima inside one object (mirror-symmetric tubes), and
+    scipy.ndimage.maximum_position picks among equal values by an unstable sort (arbitrary, not reproducible).  Scaling every
+    voxel by a factor that depends on its index makes the maxima unique without changing the character of the data."""
+    f = np.asarray(frangi, dtype=F32)
+    idx = np.arange(f.size, dtype=np.uint64).reshape(f.shape)
+    h = ((idx * np.uint64(2654435761)) % np.uint64(1 << 20)).astype(np.float64) / float(1 << 20)
+    return (f * (1.0 + h / 64.0)).astype(F32)
