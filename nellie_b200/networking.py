@@ -118,6 +118,8 @@ class NetworkEngine:
         sc = [float(v) for v in scaling]
         self.sampling = (C.c_double * 3)(*( [1.0] + sc if self.no_z else sc ))
         self.crop_voxels = 0          # of the last relabel (diagnostics)
+        self.max_crop_voxels = 1 << 28   # per group of objects: 7.5 GB of workspace
+        self._ws = None
 
     def _stream(self):
         if self.device.type != "cuda":
@@ -170,19 +172,33 @@ class NetworkEngine:
         b = boxes[keep].to(torch.int64)
         ext = b[:, 3:] - b[:, :3] + 1
         vol = ext[:, 0] * ext[:, 1] * ext[:, 2]
-        off = torch.cumsum(vol, 0) - vol
-        crops = torch.cat([keep[:, None], b[:, :3], ext, off[:, None]], dim=1).contiguous()
-        lines = torch.stack([vol // ext[:, a] for a in range(3)])                    # (3, m)
-        line_starts = (torch.cumsum(lines, 1) - lines).contiguous()
-        totals = lines.sum(1).cpu()
-        V = int(vol.sum().item())
-        self.crop_voxels = V
-        n_lines = (C.c_longlong * 3)(*[int(v) for v in totals])
-        ft_a = torch.empty(3 * V, dtype=torch.int32, device=self.device)
-        ft_b = torch.empty(3 * V, dtype=torch.int32, device=self.device)
-        stack = torch.empty(V, dtype=torch.int32, device=self.device)
-        self._call("nb200_network_relabel", _ptr(labels), _ptr(branch), nz, ny, nx, _ptr(crops), m, V, _ptr(line_starts),
-                   n_lines, self.sampling, _ptr(ft_a), _ptr(ft_b), _ptr(stack), _ptr(out), self._stream())
+        # the crops of all objects of a group lie end to end in crop space; groups keep the workspace (28 B per crop voxel)
+        # bounded when long diagonal objects have boxes as large as the frame (the reference handles one object at a time)
+        vol_host = vol.cpu().tolist()
+        groups, start, acc = [], 0, 0
+        for i, v in enumerate(vol_host):
+            if i > start and acc + v > self.max_crop_voxels:
+                groups.append((start, i))
+                start, acc = i, 0
+            acc += v
+        groups.append((start, m))
+        for g0, g1 in groups:
+            gvol, gext = vol[g0:g1], ext[g0:g1]
+            off = torch.cumsum(gvol, 0) - gvol
+            crops = torch.cat([keep[g0:g1, None], b[g0:g1, :3], gext, off[:, None]], dim=1).contiguous()
+            lines = torch.stack([gvol // gext[:, a] for a in range(3)])              # (3, objects of the group)
+            line_starts = (torch.cumsum(lines, 1) - lines).contiguous()
+            totals = lines.sum(1).cpu()
+            V = int(sum(vol_host[g0:g1]))
+            self.crop_voxels += V
+            n_lines = (C.c_longlong * 3)(*[int(v) for v in totals])
+            if self._ws is None or self._ws.numel() < 7 * V:
+                self._ws = None                                                      # release before growing
+                self._ws = torch.empty(7 * V, dtype=torch.int32, device=self.device)
+            ft_a, ft_b, stack = self._ws[:3 * V], self._ws[3 * V:6 * V], self._ws[6 * V:7 * V]
+            self._call("nb200_network_relabel", _ptr(labels), _ptr(branch), nz, ny, nx, _ptr(crops), g1 - g0, V,
+                       _ptr(line_starts), n_lines, self.sampling, _ptr(ft_a), _ptr(ft_b), _ptr(stack), _ptr(out),
+                       self._stream())
         return out
 
 

@@ -71,6 +71,8 @@ def check_relabel_against_scipy(lib, device, trials=24, seed=1):
         if trial % 7 == 0:
             scaling = (1.0,) * len(shape)
         eng = engine(lib, device, no_z, scaling)
+        if trial % 2:
+            eng.max_crop_voxels = 300                 # several groups of objects, a big object alone in its group
         out = eng.relabel(t(branch, device), t(labels, device), int(labels.max())).cpu().numpy().view(np.uint32)
         assert np.array_equal(out, P.network_relabel_objects(branch, labels, scaling)), (trial, shape, scaling)
     # nothing to do: no objects / no seeds at all
