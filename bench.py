@@ -454,10 +454,28 @@ def run_b200_arm(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": timed_launches, "output_checksum": fingerprint,
             "roofline": roofline, "roofline_kernels": roofs, "roofline_survey_groups": groups, "cpu_baseline": cpu,
             "kernel_ms_per_step": breakdown, "kernel_ms_per_sigma": per_sigma}
+    if world == 1 and args.config == 3 and not args.no_stages:
+        line["hierarchy_stages"] = stage_timings(local)
     emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def stage_timings(device_index, timeout_s=240):
+    """Markers / HuMoment features / Network device steps on one 384^3 frame, timed by scripts/bench_stages.py
+    in a SUBPROCESS after the timed region of the metric: extra evidence in the same JSON line, isolated so that nothing
+    there can disturb the measurement above (a failure is reported as text, not raised)."""
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_stages.py"), "--device", str(device_index)]
+    try:
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout_s, env=env)
+        rows = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode == 0 and rows:
+            return json.loads(rows[-1])
+        return {"error": f"rc={r.returncode}: {(r.stderr or r.stdout)[-400:]}"}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
 
 
 _REAL_STDOUT = None
@@ -488,6 +506,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-stages", action="store_true", help="skip the Markers / Hu / Network timings of scripts/bench_stages.py")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
                     help="BASELINE.json config: 3 = 1024^3 x 6 sigmas (the metric, default); 2 = 512^3 x 4 sigmas; "
