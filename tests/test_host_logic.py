@@ -240,6 +240,12 @@ def test_library_sass_uses_tma_and_packed_f32():
     assert gauss, "blur kernels not found in the library"
     for b in gauss:
         assert "DADD" in b and "DMUL" in b and "DFMA" not in b, b.split("\n")[0]
+    # the Voronoi stage of the Network relabel reproduces scipy's float64 comparisons (tie-breaking between equidistant
+    # seeds): products and sums must stay separate instructions there as well
+    voronoi = [b for b in blocks if "voronoi_stage_kernel" in b.split("\n")[0]]
+    assert voronoi, "voronoi_stage_kernel not found in the library"
+    for b in voronoi:
+        assert "DMUL" in b and "DADD" in b and "DFMA" not in b, b.split("\n")[0]
 
 
 def test_run_ladder_matches_the_reference_rules(monkeypatch):
