@@ -12,7 +12,9 @@ All of it runs in CUDA kernels behind ``include/nellie_b200.h`` (``nb200_markers
 derivative passes of ``scipy.ndimage.gaussian_laplace`` through ``nb200_gauss_axis`` / ``nb200_gauss_yx`` with order-2 taps);
 the outputs are bit-identical to the reference's.  Only the full-volume branch is reproduced — the reference's own test
 (tests/test_mocap_marking.py) asserts that its chunked low-memory branch gives the same result; ``low_memory`` /
-``max_chunk_voxels`` are accepted and ignored.  There is no CPU path: ``device='cpu'`` raises.
+``max_chunk_voxels`` are accepted and ignored.  There is no CPU path: ``device='cpu'`` raises.  One pathological input
+differs: a label frame without a single background voxel gets the clamp as distance everywhere, where scipy measures to the
+virtual voxel (-1, -1, -1).
 """
 from __future__ import annotations
 
