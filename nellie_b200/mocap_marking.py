@@ -183,7 +183,7 @@ class MarkerEngine:
 class Markers:
     def __init__(self, im_info, num_t=None, min_radius_um=0.20, max_radius_um=1, use_im="distance", num_sigma=5,
                  viewer=None, prefer_gpu=True, peak_min_distance=2, device="auto", low_memory=False,
-                 max_chunk_voxels=int(1e6), cuda_device=None, t_shard=None, fallback=None):
+                 max_chunk_voxels=int(1e6), cuda_device=None, t_shard=None, fallback=None, z_shard=None):
         dev = (device or "auto").lower()
         if dev == "cpu" or (dev == "auto" and not prefer_gpu):
             raise ValueError("nellie_b200.Markers implements the CUDA path only; device='cpu' belongs to "
@@ -227,6 +227,14 @@ class Markers:
         self.truncate = 4.0
         self._cuda_device = cuda_device
         self.t_shard = None if t_shard is None else (int(t_shard[0]), int(t_shard[1]))
+        # Z-sharding (rank, world) of every frame (for frames too large for one GPU): the stage has no global
+        # step, so rank r runs the ordinary single-GPU sequence on its planes plus a halo and keeps its own planes
+        # (_z_extent); no collective, the ranks only share the output files
+        self.z_shard = None if z_shard is None else (int(z_shard[0]), int(z_shard[1]))
+        if self.z_shard is not None and t_shard is not None:
+            raise ValueError("a Markers stage is sharded over T or over Z, not both")
+        if self.z_shard is not None and im_info.no_z:
+            raise ValueError("2-D frames are T-sharded; Z-sharding needs a Z axis")
         self.fallback = fallback
         self._engine = None
         self._ctor_kwargs = dict(num_t=num_t, min_radius_um=min_radius_um, max_radius_um=max_radius_um, use_im=use_im,
@@ -272,12 +280,11 @@ class Markers:
         self.im_memmap = self.im_info.get_memmap(self.im_info.im_path)
         self.shape = self.label_memmap.shape
         self.im_frangi_memmap = self.im_info.get_memmap(paths["im_preprocessed"]) if self.use_im == "frangi" else None
-        self.im_marker_memmap = allocate_shared_output(self.im_info, paths["im_marker"], "uint8", "mocap marker image",
-                                                       self.t_shard)
+        shard = self.t_shard or self.z_shard
+        self.im_marker_memmap = allocate_shared_output(self.im_info, paths["im_marker"], "uint8", "mocap marker image", shard)
         self.im_distance_memmap = allocate_shared_output(self.im_info, paths["im_distance"], "float32",
-                                                         "distance transform image", self.t_shard)
-        self.im_border_memmap = allocate_shared_output(self.im_info, paths["im_border"], "uint8", "border image",
-                                                       self.t_shard)
+                                                         "distance transform image", shard)
+        self.im_border_memmap = allocate_shared_output(self.im_info, paths["im_border"], "uint8", "border image", shard)
 
     # ---- device plumbing ------------------------------------------------------------------------------------------------
     def _torch_device(self):
@@ -371,16 +378,42 @@ class Markers:
             return eng.run_frame(self._labels_dev(labels), self._dev(intensity, torch.float32),
                                  self._dev(frangi, torch.float32) if self.use_im == "frangi" else None)
 
+    def z_halo(self):
+        """Planes a Z slab needs beyond its own for its own planes to come out exactly as in the whole frame: the kept
+        peaks of a plane depend on peaks within ``d`` planes (suppression window), those on the response within one more
+        plane (3^d maximum), the response on the distance image within the Z radius of the widest kernel, and the clamped
+        distance on the label field within the scan window.  Reflection at the slab's own ends only touches planes
+        outside that chain; at the frame's ends the slab's end IS the frame's end."""
+        if not self.sigmas:
+            self._set_default_sigmas()
+        clamp = float(np.float32(float(self.max_radius_px) * 2.0))
+        window = max(1, int(math.ceil(clamp)))
+        rz = max(int(self.truncate * (float(s) / self.z_ratio) + 0.5) for s in self.sigmas)
+        return window + rz + int(self.peak_min_distance) + 1
+
+    def _z_extent(self, nz):
+        """(first plane, last plane + 1) of the slab this rank computes and of the part it owns."""
+        from .sharding import z_partition
+        rank, world = self.z_shard
+        z0, z1 = z_partition(nz, world)[rank]
+        h = self.z_halo()
+        return max(0, z0 - h), min(nz, z1 + h), z0, z1
+
     def _run_frame_impl(self, t, low_memory=False, chunk_voxels=None):
-        """mocap_marking.py:648-703: numpy (marker uint8, distance float32, border uint8) of frame ``t``."""
+        """mocap_marking.py:648-703: numpy (marker uint8, distance float32, border uint8) of frame ``t`` — of this rank's
+        own planes when the stage is Z-sharded."""
         logger.info("Running motion capture marking, volume %s/%s", t, (self.num_t or 1) - 1)
-        frangi = None
-        if self.use_im == "frangi":
-            if self.im_frangi_memmap is None:
-                raise RuntimeError("Frangi image requested for peak detection but not available.")
-            frangi = self.im_frangi_memmap[t]
-        marker, distance, border = self.marker_frame_device(self.label_memmap[t], self.im_memmap[t], frangi)
-        return marker.cpu().numpy(), distance.cpu().numpy(), border.cpu().numpy()
+        if self.use_im == "frangi" and self.im_frangi_memmap is None:
+            raise RuntimeError("Frangi image requested for peak detection but not available.")
+        if self.z_shard is None:
+            frangi = self.im_frangi_memmap[t] if self.use_im == "frangi" else None
+            marker, distance, border = self.marker_frame_device(self.label_memmap[t], self.im_memmap[t], frangi)
+            return marker.cpu().numpy(), distance.cpu().numpy(), border.cpu().numpy()
+        e0, e1, z0, z1 = self._z_extent(int(self.label_memmap.shape[1]))
+        frangi = self.im_frangi_memmap[t, e0:e1] if self.use_im == "frangi" else None
+        marker, distance, border = self.marker_frame_device(self.label_memmap[t, e0:e1], self.im_memmap[t, e0:e1], frangi)
+        own = slice(z0 - e0, z1 - e0)
+        return marker[own].cpu().numpy(), distance[own].cpu().numpy(), border[own].cpu().numpy()
 
     def _run_frame(self, t):
         return self._run_frame_impl(t)
@@ -396,13 +429,14 @@ class Markers:
                 self.viewer.status = f"Mocap marking. Frame: {t + 1} of {self.num_t}."
             results = self._run_frame(t)
             whole = self.im_marker_memmap.shape != self.shape and self.im_info.no_t      # mocap_marking.py:767
+            own = slice(None) if self.z_shard is None else slice(*self._z_extent(int(self.label_memmap.shape[1]))[2:])
             for mm, frame in zip(outs, results):
                 if mm is None:
                     continue
                 if whole:
-                    mm[:] = frame
+                    mm[own] = frame
                 else:
-                    parallel_copyto(mm[t], frame)
+                    parallel_copyto(mm[t][own], frame)
                 if hasattr(mm, "flush"):
                     mm.flush()
 

@@ -226,3 +226,35 @@ def check_mirror_class_helpers_and_run_on_files(make_markers, tmp_path):
             assert np.array_equal(info.get_memmap(info.pipeline_paths["im_marker"])[t], expect[t][0])
             assert np.array_equal(info.get_memmap(info.pipeline_paths["im_distance"])[t], expect[t][1])
             assert np.array_equal(info.get_memmap(info.pipeline_paths["im_border"])[t], expect[t][2])
+
+
+def check_z_sharded_equals_whole_frame(make_markers, tmp_path, world=3):
+    """Markers(z_shard=(r, world)) for every r on shared files: slabs + halo through the ordinary single-GPU sequence, own
+    planes written — identical to the oracle on the whole frame (tall frame, several objects crossing the slab seams,
+    kernels wide enough that every term of the halo matters)."""
+    from nellie_b200.imio import StackInfo
+    from oracle import pipeline as P
+    rng = np.random.default_rng(77)
+    shape = (96, 36, 40)
+    labels = np.zeros(shape, np.int32)
+    labels[blob_mask(shape, rng, n_blobs=14, r_max=9.0)] = 1
+    labels[blob_mask(shape, rng, n_blobs=3, r_max=16.0)] = 2
+    zz, yy, xx = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+    labels[(zz - 33) ** 2 + (yy - 18) ** 2 + (xx - 20) ** 2 <= 17 ** 2] = 3      # thick object across the first seam
+    raw = np.round(rng.random(shape) * 50 + 300 * (labels > 0) * rng.random(shape)).astype(np.uint16)
+    dim_res = {"X": 0.2, "Y": 0.2, "Z": 0.25, "T": 1.0}
+    info = StackInfo.from_array(raw[None], "TZYX", dim_res, str(tmp_path))
+    info.allocate_memory(info.pipeline_paths["im_instance_label"], dtype="int32", data=labels[None])
+    halos = set()
+    for r in range(world):
+        m = make_markers(info, z_shard=(r, world))
+        m.run()
+        halos.add(m.z_halo())
+        e0, e1, z0, z1 = m._z_extent(shape[0])
+        assert e0 <= z0 < z1 <= e1 and (e1 - e0) < shape[0]            # a real slab, not the whole frame
+    assert len(halos) == 1
+    ref = P.marker_frame(raw, labels, P.MarkerSpec(dim_res=dim_res))
+    assert ref[0].sum() > 20 and ref[1].max() == 10.0                   # markers exist, the distance clamp is active
+    assert np.array_equal(info.get_memmap(info.pipeline_paths["im_marker"])[0], ref[0])
+    assert np.array_equal(info.get_memmap(info.pipeline_paths["im_distance"])[0], ref[1])
+    assert np.array_equal(info.get_memmap(info.pipeline_paths["im_border"])[0], ref[2])

@@ -114,6 +114,10 @@ def test_mirror_class_helpers_and_run_on_files(emu, tmp_path):
     K.check_mirror_class_helpers_and_run_on_files(_emu_markers(emu), tmp_path)
 
 
+def test_z_sharded_markers_equal_the_whole_frame(emu, tmp_path):
+    K.check_z_sharded_equals_whole_frame(_emu_markers(emu), tmp_path)
+
+
 def test_markers_refuses_cpu_and_unknown_images():
     from nellie_b200.mocap_marking import Markers
     info = SimpleNamespace(no_t=True, no_z=True, shape=(1, 9, 9), axes="TYX", dim_res={"X": 0.2, "Y": 0.2})

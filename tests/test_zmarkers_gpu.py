@@ -69,6 +69,11 @@ def test_mirror_class_helpers_and_run_on_files(cuda, tmp_path):
     K.check_mirror_class_helpers_and_run_on_files(Markers, tmp_path)
 
 
+def test_z_sharded_markers_equal_the_whole_frame(cuda, tmp_path):
+    from nellie_b200.mocap_marking import Markers
+    K.check_z_sharded_equals_whole_frame(Markers, tmp_path)
+
+
 def test_markers_frame_of_production_size_matches_oracle(cuda):
     """A 96 x 320 x 384 frame (1.2e7 voxels: every grid-stride loop wraps many times) of labelled tubes and blobs."""
     from types import SimpleNamespace
