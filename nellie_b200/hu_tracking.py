@@ -226,8 +226,7 @@ class HuMomentFeatures:
         a = np.asarray(arr)
         if not a.dtype.isnative:
             a = a.astype(a.dtype.newbyteorder("="))
-        if a.dtype == np.uint16:
-            a = a.astype(np.int32)
+        # uint8 / uint16 frames travel in their own type and are cast on the device
         t = torch.from_numpy(np.ascontiguousarray(a)).to(self._torch_device())
         return t.to(torch.float32).contiguous()
 

@@ -313,10 +313,9 @@ class Markers:
         a = np.asarray(arr)
         if not a.dtype.isnative:
             a = a.astype(a.dtype.newbyteorder("="))
-        if a.dtype == np.uint16:
-            a = a.astype(np.int32)
-        elif a.dtype in (np.uint32, np.uint64):
+        if a.dtype in (np.uint32, np.uint64):
             a = a.astype(np.int64)
+        # uint16 frames travel as uint16 (half the bytes of a host-side widening) and are cast on the device
         t = torch.from_numpy(np.ascontiguousarray(a)).to(self._torch_device())
         return t.to(dtype).contiguous()
 

@@ -207,6 +207,14 @@ def check_mirror_class_helpers_and_run_on_files(make_markers, tmp_path):
     kept = m._remove_close_peaks(coords, g["raw"])
     assert np.array_equal(kept, np.argwhere(g["marker"]))
     assert m._remove_close_peaks(coords[:0], g["raw"]).size == 0
+    # uint16 raw frame and int32 labels straight from the fixture through _run_frame_impl (native-dtype upload)
+    mu = make_markers(SimpleNamespace(no_t=True, no_z=False, shape=(1,) + g2["raw"].shape, axes="TZYX",
+                                      dim_res=g2["meta"]["dim_res"]), num_t=1)
+    mu.im_memmap, mu.label_memmap = g2["raw"][None], g2["labels"][None]
+    mu.shape = mu.label_memmap.shape
+    got = mu._run_frame_impl(0)
+    assert g2["raw"].dtype == np.uint16
+    assert all(np.array_equal(a, g2[k]) for a, k in zip(got, ("marker", "distance", "border")))
     # run() on files: a two-frame stack (same shape: crop both inputs)
     shp = tuple(min(a, b) for a, b in zip(g["raw"].shape, g2["raw"].shape))
     sl = tuple(slice(0, s) for s in shp)

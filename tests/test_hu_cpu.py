@@ -140,6 +140,15 @@ def test_mirror_class_on_emulated_kernels(emu):
     low.im_distance_memmap, low.im_marker_memmap = m.im_distance_memmap, m.im_marker_memmap
     ff = low._get_frame_features(0)
     assert np.array_equal(ff.stats, g["stats_stream"]) and ff.hu.dtype == np.float32
+    # a uint16 raw frame travels in its own type and takes numpy's integer rules on the device
+    gu = K.load_hu_case("hu_sample_crop")
+    assert gu["raw"].dtype == np.uint16
+    iu = SimpleNamespace(no_t=False, no_z=False, shape=(2,) + gu["raw"].shape, axes="TZYX", dim_res=gu["meta"]["dim_res"])
+    mu = Emu(iu, num_t=2, dense_limit=int(5e7))
+    mu.im_memmap, mu.im_frangi_memmap = gu["raw"][None], gu["frangi"][None]
+    mu.im_distance_memmap, mu.im_marker_memmap = gu["distance"][None], gu["marker"][None]
+    fu = mu._get_frame_features(0)
+    assert np.array_equal(fu.stats, gu["stats_dense"]) and np.allclose(fu.hu, gu["hu_dense"], rtol=1e-9, atol=1e-9)
     with pytest.raises(ValueError):
         H.HuMomentFeatures(info, device="cpu")
     with pytest.raises(NotImplementedError):
