@@ -55,6 +55,9 @@ class MarkerEngine:
                  truncate=4.0):
         self.lib = _cabi.load() if lib is None else lib
         self.device = torch.device(device)
+        if lib is None and self.device.type != "cuda":
+            raise RuntimeError("nellie_b200 has no CPU path: %s needs a CUDA device (a host device is only accepted "
+                               "together with the test suite's emulated kernel library)" % type(self).__name__)
         self.shape = tuple(int(s) for s in frame_shape)
         self.no_z = bool(no_z)
         if self.no_z:

@@ -114,6 +114,9 @@ class NetworkEngine:
     def __init__(self, no_z, scaling, device, lib=None):
         self.lib = _cabi.load() if lib is None else lib
         self.device = torch.device(device)
+        if lib is None and self.device.type != "cuda":
+            raise RuntimeError("nellie_b200 has no CPU path: %s needs a CUDA device (a host device is only accepted "
+                               "together with the test suite's emulated kernel library)" % type(self).__name__)
         self.no_z = bool(no_z)
         sc = [float(v) for v in scaling]
         self.sampling = (C.c_double * 3)(*( [1.0] + sc if self.no_z else sc ))

@@ -318,3 +318,16 @@ def test_gate_threshold_reproduces_numpy_comparison_semantics():
         assert np.array_equal(xf > np.float64(t), xf > np.float32(g(np.float64(t), np.float32)))
         assert np.array_equal(xf > float(t), xf > np.float32(g(float(t), np.float32)))
         assert np.array_equal(xf > np.float32(t), xf > np.float32(g(np.float32(t), np.float32)))
+
+
+def test_stage_engines_refuse_a_host_device():
+    """The engine classes of the widened stages take ``lib=`` / ``device=`` so that the tests can inject the host-emulated
+    kernel library; without an injected library a host device is an error (no CPU path in the product)."""
+    from nellie_b200.hu_tracking import HuFeatureEngine
+    from nellie_b200.mocap_marking import MarkerEngine
+    from nellie_b200.networking import NetworkEngine
+    for make in (lambda: MarkerEngine((4, 5, 6), False, [1.0], 1.0, 5.0, 2, "cpu"),
+                 lambda: HuFeatureEngine((4, 5, 6), False, "cpu"),
+                 lambda: NetworkEngine(False, (1.0, 1.0, 1.0), "cpu")):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            make()
