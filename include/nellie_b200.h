@@ -349,6 +349,9 @@ int nb200_remove_connected_label_pixels(const int* labels, int nz, int ny, int n
  * nb200_markers_peak_update: one scale of :496-505 — a voxel with mask != 0, distance > 0, resp equal to the maximum of its
  *   3^d neighbourhood (clamped at the frame border) and resp > best gets best = resp, peak = 1.  best / peak are zeroed by
  *   the caller before the first scale.
+ * nb200_markers_peak_update_fused: nb200_markers_log_response + nb200_markers_peak_update in one kernel without the response
+ *   volume (the response is re-evaluated from d0, d1, d2 where it is needed: mask voxels and the neighbours of candidates);
+ *   identical best / peak.  This is what the stage runs; the two-step form remains for callers that want the response.
  * nb200_markers_nms: :595-606 — marker = 1 where peak != 0, intensity > 0 and no peak inside the (2*radius+1)^d window
  *   (clamped at the frame border) has a larger intensity; equal intensities keep each other, as the reference's
  *   score == maximum_filter(score) does.  intensity: the raw frame as float32 (the cast of score_img[...] = intensity). */
@@ -360,6 +363,9 @@ int nb200_markers_log_response(const float* d0, const float* d1, const float* d2
                                float* resp, void* stream);
 int nb200_markers_peak_update(const float* resp, const unsigned char* mask, const float* distance, int nz, int ny, int nx,
                               float* best, unsigned char* peak, void* stream);
+int nb200_markers_peak_update_fused(const float* d0, const float* d1, const float* d2, float sigma_sq,
+                                    const unsigned char* mask, const float* distance, int nz, int ny, int nx, float* best,
+                                    unsigned char* peak, void* stream);
 int nb200_markers_nms(const unsigned char* peak, const float* intensity, int nz, int ny, int nx, int radius,
                       unsigned char* marker, void* stream);
 

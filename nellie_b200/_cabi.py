@@ -86,6 +86,7 @@ _SIGS = {
     "nb200_markers_edt": ([_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _p, _p, _p], C.c_int),
     "nb200_markers_log_response": ([_p, _p, _p, _ll, C.c_float, _p, _p], C.c_int),
     "nb200_markers_peak_update": ([_p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p], C.c_int),
+    "nb200_markers_peak_update_fused": ([_p, _p, _p, C.c_float, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p], C.c_int),
     "nb200_markers_nms": ([_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_hu_frangi_transform": ([_p, _ll, _p, _p, _p], C.c_int),
     "nb200_hu_distance_max": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),

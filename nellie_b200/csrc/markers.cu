@@ -196,6 +196,45 @@ peak_update_kernel(const float* __restrict__ resp, const unsigned char* __restri
     }
 }
 
+// The same step without the response volume: the response of a voxel is three loads and three float32 operations, so the
+// kernel evaluates it where it is needed — at the mask voxels, and at the 26 neighbours of those whose own response beats
+// the best scale so far — instead of streaming a float32 volume out and in again (25 -> ~3 B/voxel for a 10 % mask).
+__device__ __forceinline__ float response_at(const float* __restrict__ d0, const float* __restrict__ d1,
+                                             const float* __restrict__ d2, long long idx, float sigma_sq) {
+    float lap = d0[idx] + d1[idx];
+    if (d2) lap = lap + d2[idx];
+    float r = (-lap) * sigma_sq;
+    if (r < 0.0f) r = 0.0f;
+    return r;
+}
+
+__global__ void __launch_bounds__(THREADS)
+peak_update_fused_kernel(const float* __restrict__ d0, const float* __restrict__ d1, const float* __restrict__ d2,
+                         float sigma_sq, const unsigned char* __restrict__ mask, const float* __restrict__ distance, Dims d,
+                         float* __restrict__ best, unsigned char* __restrict__ peak) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < d.total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        if (!mask[idx] || !(distance[idx] > 0.0f)) continue;
+        const float r = response_at(d0, d1, d2, idx, sigma_sq);
+        if (!(r > best[idx])) continue;
+        const Pos p = pos_of(idx, d);
+        const int z0 = p.z > 0 ? -1 : 0, z1 = p.z + 1 < d.nz ? 1 : 0;
+        const int y0 = p.y > 0 ? -1 : 0, y1 = p.y + 1 < d.ny ? 1 : 0;
+        const int x0 = p.x > 0 ? -1 : 0, x1 = p.x + 1 < d.nx ? 1 : 0;
+        bool is_max = true;
+        for (int dz = z0; dz <= z1 && is_max; ++dz)
+            for (int dy = y0; dy <= y1 && is_max; ++dy) {
+                const long long row = idx + dz * d.plane + (long long)dy * d.nx;
+                for (int dx = x0; dx <= x1; ++dx)
+                    if (response_at(d0, d1, d2, row + dx, sigma_sq) > r) is_max = false;
+            }
+        if (is_max) {
+            best[idx] = r;
+            peak[idx] = 1;
+        }
+    }
+}
+
 // ---- non-maximum suppression on the raw intensity ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS)
 nms_kernel(const unsigned char* __restrict__ peak, const float* __restrict__ intensity, Dims d, int radius,
@@ -279,6 +318,17 @@ int nb200_markers_peak_update(const float* resp, const unsigned char* mask, cons
     const Dims d = make_dims(nz, ny, nx);
     NB_LAUNCH(peak_update_kernel, grid_of(d.total), THREADS, nb::as_stream(stream), resp, mask, distance, d, best, peak);
     return nb::check_launch("peak_update_kernel");
+}
+
+int nb200_markers_peak_update_fused(const float* d0, const float* d1, const float* d2, float sigma_sq,
+                                    const unsigned char* mask, const float* distance, int nz, int ny, int nx, float* best,
+                                    unsigned char* peak, void* stream) {
+    NB_REQUIRE(d0 && d1 && mask && distance && best && peak && dims_ok(nz, ny, nx), NB200_ERR_ARG,
+               "nb200_markers_peak_update_fused: bad argument");
+    const Dims d = make_dims(nz, ny, nx);
+    NB_LAUNCH(peak_update_fused_kernel, grid_of(d.total), THREADS, nb::as_stream(stream), d0, d1, d2, sigma_sq, mask,
+              distance, d, best, peak);
+    return nb::check_launch("peak_update_fused_kernel");
 }
 
 int nb200_markers_nms(const unsigned char* peak, const float* intensity, int nz, int ny, int nx, int radius,

@@ -155,14 +155,19 @@ class MarkerEngine:
         self._yx(self.t[1], self.d[2], w0y, w2x, r, self.t[2])
         return self.d[0], self.d[1], self.d[2]
 
-    def peaks(self, base):
-        """mocap_marking.py:452-512 (_local_max_peak): fills ``peak`` (uint8) and ``best``."""
+    def peaks(self, base, fused=True):
+        """mocap_marking.py:452-512 (_local_max_peak): fills ``peak`` (uint8) and ``best``.  ``fused`` (default): response
+        and local-maximum test in one kernel, no response volume; ``fused=False``: the two-step form (same result)."""
         st = self._stream()
         self.best.zero_()
         self.peak.zero_()
         for s, taps in zip(self.sigmas, self.taps):
             d0, d1, d2 = self.laplace_terms(base, taps)
             sigma_sq = C.c_float(float(np.float32(s ** 2)))       # float32 array * python float (mocap_marking.py:490)
+            if fused:
+                self._call("nb200_markers_peak_update_fused", _ptr(d0), _ptr(d1), _ptr(d2), sigma_sq, _ptr(self.mask),
+                           _ptr(self.distance), self.nz, self.ny, self.nx, _ptr(self.best), _ptr(self.peak), st)
+                continue
             self._call("nb200_markers_log_response", _ptr(d0), _ptr(d1), _ptr(d2), self.n, sigma_sq, _ptr(d0), st)
             self._call("nb200_markers_peak_update", _ptr(d0), _ptr(self.mask), _ptr(self.distance), self.nz, self.ny,
                        self.nx, _ptr(self.best), _ptr(self.peak), st)

@@ -7,7 +7,8 @@ frame, device-resident, CUDA events.  Prints ONE JSON line.  `bench.py` runs thi
 The frame goes through the repo's own Filter and Label first (so the label field is what the stages see in production).
 Skeletonization is a scikit-image host call in the reference and here (not timed, not available in this image): the Network
 steps run on a stand-in skeleton, the ridge of the distance transform, computed with torch ops.
-Algorithmic bytes per voxel: mask + border + distance transform 19, one Markers scale 56.
+Algorithmic bytes per voxel: mask + border + distance transform 19, one Markers scale 43 (five blur passes of
+8 B + the fused response / maximum test).
 """
 from __future__ import annotations
 
@@ -76,6 +77,8 @@ def main():
     raw_f = raw.contiguous()
     timed("markers.mask_border_distance", lambda: meng.distance_and_border(labels))
     timed("markers.peaks_all_scales", lambda: meng.peaks(meng.distance))
+    timed("markers.peaks_all_scales_two_step", lambda: meng.peaks(meng.distance, fused=False))
+    meng.peaks(meng.distance)
     timed("markers.suppress", lambda: meng.suppress(meng.peak, raw_f))
     timed("markers.frame", lambda: meng.run_frame(labels, raw_f))
     n_markers = int(meng.marker.sum().item())
@@ -122,7 +125,7 @@ def main():
         "voxels_per_s": {"markers.frame": vox / (times["markers.frame"] * 1e-3),
                          "network.device_steps": vox / (1e-3 * sum(v for k, v in times.items() if k.startswith("network.")))},
         "hbm_frac_of_peak": {"markers.mask_border_distance (19 B/voxel)": frac(19.0, times["markers.mask_border_distance"]),
-                             "markers.peaks_all_scales (56 B/voxel and scale)": frac(56.0 * n_scales, times["markers.peaks_all_scales"])},
+                             "markers.peaks_all_scales (43 B/voxel and scale)": frac(43.0 * n_scales, times["markers.peaks_all_scales"])},
         "peak_gbs": peak,
     }
     print(json.dumps(line), flush=True)

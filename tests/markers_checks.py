@@ -144,6 +144,8 @@ def check_peaks_and_nms(be: Backend, shape, z_res):
     assert ref_peak.sum() > 10
     assert np.array_equal(peak, ref_peak)
     assert np.array_equal(_np(eng.best), ref_best)
+    two_step = _np(eng.peaks(base_t, fused=False)).astype(bool)             # response volume + separate maximum test
+    assert np.array_equal(two_step, ref_peak) and np.array_equal(_np(eng.best), ref_best)
     for s, taps in zip(eng.sigmas, eng.taps):
         d0, d1, d2 = eng.laplace_terms(base_t, taps)
         r = be.empty(shape, torch.float32)
