@@ -268,3 +268,38 @@ def check_z_sharded_equals_whole_frame(make_markers, tmp_path, world=3):
     assert np.array_equal(info.get_memmap(info.pipeline_paths["im_marker"])[0], ref[0])
     assert np.array_equal(info.get_memmap(info.pipeline_paths["im_distance"])[0], ref[1])
     assert np.array_equal(info.get_memmap(info.pipeline_paths["im_border"])[0], ref[2])
+
+
+OPTION_CASES = [
+    dict(no_z=False, kw=dict(peak_min_distance=0)),
+    dict(no_z=False, kw=dict(num_sigma=1, peak_min_distance=1)),
+    dict(no_z=False, kw=dict(min_radius_um=0.6, max_radius_um=0.5)),            # non-positive sigma range: one scale
+    dict(no_z=False, kw=dict(use_im="frangi", max_radius_um=0.7), z_res=0.1),
+    dict(no_z=True, kw=dict(use_im="frangi", num_sigma=2, peak_min_distance=4)),
+    dict(no_z=True, kw=dict(max_radius_um=2.0, num_sigma=8)),                   # radii up to 26: per-axis blur path
+    dict(no_z=False, kw=dict(), z_res=0.45),                                    # Z sigma 0.22 .. 0.64: radius-1 .. 3 Z kernels
+    dict(no_z=False, kw=dict(num_sigma=2), z_res=0.9),                          # Z sigma 0.11: a radius-0 Z kernel (one tap)
+]
+
+
+def check_option_matrix(be: Backend, case):
+    """Constructor options of the reference class that change the kernel sequence (scale list, image used for the peaks,
+    suppression radius, anisotropy), each against the oracle on one small frame with uint8 intensities (many ties)."""
+    from oracle import pipeline as P
+    no_z = case["no_z"]
+    shape = (44, 52) if no_z else (14, 30, 34)
+    rng = np.random.default_rng(len(str(case)))
+    labels = np.zeros(shape, np.int32)
+    labels[blob_mask(shape, rng, n_blobs=7, r_max=8.0)] = 1
+    labels[blob_mask(shape, rng, n_blobs=2, r_max=12.0)] = 5
+    raw = rng.integers(0, 6, shape).astype(np.uint8)
+    frangi = (rng.random(shape).astype(np.float32) * (labels > 0)).astype(np.float32)
+    dim_res = {"X": 0.1, "Y": 0.1, "Z": None if no_z else case.get("z_res", 0.13), "T": 1.0}
+    spec = P.MarkerSpec(dim_res=dim_res, no_z=no_z, **case["kw"])
+    ref = P.marker_frame(raw, labels, spec, frangi=frangi)
+    eng = be.engine(shape, no_z, spec)
+    got = eng.run_frame(be.t(labels, np.int32), be.t(raw, np.float32),
+                        be.t(frangi, np.float32) if spec.use_im == "frangi" else None)
+    for g, r, name in zip(got, ref, ("marker", "distance", "border")):
+        assert np.array_equal(_np(g), r), (name, case)
+    assert ref[0].sum() > 0

@@ -106,6 +106,11 @@ def test_emulated_peaks_and_nms_match_oracle(emu, shape, z_res):
     K.check_peaks_and_nms(emu, shape, z_res)
 
 
+@pytest.mark.parametrize("case", K.OPTION_CASES, ids=lambda c: ",".join(f"{k}={v}" for k, v in c["kw"].items()) or "aniso")
+def test_emulated_option_matrix_matches_oracle(emu, case):
+    K.check_option_matrix(emu, case)
+
+
 def test_mirror_class_replays_reference_marker_tests(emu):
     K.check_mirror_class_replays_reference_tests(_emu_markers(emu))
 

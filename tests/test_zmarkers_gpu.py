@@ -59,6 +59,11 @@ def test_peaks_and_nms_match_oracle(cuda, shape, z_res):
     K.check_peaks_and_nms(cuda, shape, z_res)
 
 
+@pytest.mark.parametrize("case", K.OPTION_CASES, ids=lambda c: ",".join(f"{k}={v}" for k, v in c["kw"].items()) or "aniso")
+def test_option_matrix_matches_oracle(cuda, case):
+    K.check_option_matrix(cuda, case)
+
+
 def test_mirror_class_replays_reference_marker_tests(cuda):
     from nellie_b200.mocap_marking import Markers
     K.check_mirror_class_replays_reference_tests(Markers)
