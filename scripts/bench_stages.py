@@ -29,7 +29,6 @@ def main():
     ap.add_argument("--device", type=int, default=int(os.environ.get("LOCAL_RANK", "0")))
     args = ap.parse_args()
 
-    import numpy as np
     import torch
     import torch.nn.functional as F
 
