@@ -424,6 +424,17 @@ int nb200_network_relabel(const int* labels, const int* branch, int nz, int ny, 
                           long long crop_voxels, const long long* line_starts, const long long* n_lines,
                           const double* sampling, int* ft_a, int* ft_b, int* stack, unsigned int* out, void* stream);
 
+/* ---- Label thresholds with histogram_nbins != 256 (labelling.py:23-35, :440-465; gpu_functions.py:23-94) ---------------------
+ * General-bin-count form of nb200_hist_bins + nb200_finalize_label_threshold / nb200_hist_bins_f64 + nb200_finalize_otsu_f64
+ * (those are specialised for the reference default of 256 and stay the production path).  state: after nb200_hist_reset +
+ * nb200_hist_minmax over the same `vals` (transform NONE, or LOG10 when log_domain != 0).  f64_edges != 0: the samples are an
+ * integer frame's values (np.histogram then bins with float64 edges; log_domain must be 0).  otsu_only != 0: out[0] = the Otsu
+ * bin centre (the intensity threshold of labelling.py:457-465); otherwise out[] is laid out as nb200_finalize_label_threshold
+ * writes it.  workspace: nb200_histn_workspace_bytes(nbins) bytes, 8-byte aligned.  2 <= nbins <= 2^24. */
+size_t nb200_histn_workspace_bytes(int nbins);
+int nb200_histn_threshold(const float* vals, long long n, int log_domain, int f64_edges, int otsu_only, int nbins,
+                          const long long* state, void* workspace, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,8 @@ _SIGS = {
     "nb200_network_object_boxes": ([_p, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p], C.c_int),
     "nb200_network_relabel": ([_p, _p, C.c_int, C.c_int, C.c_int, _p, _ll, _ll, _p, C.POINTER(_ll), C.POINTER(C.c_double),
                                _p, _p, _p, _p, _p], C.c_int),
+    "nb200_histn_workspace_bytes": ([C.c_int], C.c_size_t),
+    "nb200_histn_threshold": ([_p, _ll, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p], C.c_int),
     "nb200_remove_edges": ([_p, C.c_int, C.c_int, C.c_int, C.c_int, _p], C.c_int),
     "nb200_fold_records": ([_p, C.c_int, C.c_int, _p, _p], C.c_int),
     "nb200_fold_records_n": ([_p, C.c_int, C.c_int, C.c_int, _p, _p], C.c_int),

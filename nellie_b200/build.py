@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libnellie_b200.so")
-SOURCES = ["cabi.cu", "gauss.cu", "thresholds.cu", "frangi.cu", "hessian_fast.cu", "sparse.cu", "finalize.cu", "label.cu", "log2d.cu", "markers.cu", "hu.cu", "network.cu"]
+SOURCES = ["cabi.cu", "gauss.cu", "thresholds.cu", "frangi.cu", "hessian_fast.cu", "sparse.cu", "finalize.cu", "label.cu", "log2d.cu", "markers.cu", "hu.cu", "network.cu", "histn.cu"]
 HEADERS = ["common.cuh", "devmath.cuh", "hessian.cuh", "hessian_march.cuh", "march_host.cuh", os.path.join("..", "..", "include", "nellie_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
               "-std=c++17", "-Xcompiler", "-fPIC",

@@ -53,8 +53,9 @@ def gate_threshold_f32(thresh, data_dtype) -> float:
 class LabelEngine:
     """Device buffers + kernel sequence for frames of one shape on one GPU."""
 
-    def __init__(self, frame_shape, no_z, min_area, sampling_pixels, device):
+    def __init__(self, frame_shape, no_z, min_area, sampling_pixels, device, nbins=256):
         self.lib = _cabi.load()
+        self.nbins = int(nbins)          # labelling.py:23-35 histogram_nbins; 256 = the production kernels of thresholds.cu
         self.device = torch.device(device)
         self.shape = tuple(int(s) for s in frame_shape)
         if no_z:
@@ -77,6 +78,10 @@ class LabelEngine:
         self.hist = torch.zeros(_cabi.HIST_WORDS, dtype=torch.int64, device=dev)
         self.thr = torch.zeros(7, dtype=torch.float64, device=dev)
         self.launches = 0
+        self._hist_vals = None           # (sample buffer, count) of the last _hist_of call: the general-bin path re-reads it
+        self._histn_ws = None
+        if self.nbins != 256:
+            self._histn_ws = torch.empty(int(self.lib.nb200_histn_workspace_bytes(self.nbins)), dtype=torch.uint8, device=dev)
 
     def _call(self, name, *args):
         self.launches += 1
@@ -86,6 +91,9 @@ class LabelEngine:
         st = _stream()
         self._call("nb200_hist_reset", _ptr(self.hist), st)
         self._call("nb200_hist_minmax", _ptr(vals), n, transform, None, _ptr(self.hist), st)
+        self._hist_vals = (vals, n)
+        if self.nbins != 256:
+            return   # bins + thresholds in one call later (nb200_histn_threshold)
         if f64:      # integer frame: numpy bins with float64 edges
             self._call("nb200_hist_bins_f64", _ptr(vals), n, _ptr(self.hist), st)
         else:
@@ -112,11 +120,20 @@ class LabelEngine:
         self._hist_of(full, self.n, transform, f64)
         return int(self.hist[2].item())
 
+    def _histn(self, log_domain, f64, otsu_only):
+        """Bins + thresholds of the last sampled buffer for histogram_nbins != 256 (csrc/histn.cu)."""
+        vals, n = self._hist_vals
+        self._call("nb200_histn_threshold", _ptr(vals), n, int(log_domain), int(f64), int(otsu_only), self.nbins,
+                   _ptr(self.hist), _ptr(self._histn_ws), _ptr(self.thr), _stream())
+
     def frangi_threshold(self, frangi, gate=None, gate_thresh=None):
         """labelling.py:440-455; returns the float32 threshold as a Python float, or None."""
         self._sample_hist(frangi, _cabi.TF_LOG10, gate if gate_thresh is not None else None,
                           0.0 if gate_thresh is None else gate_thresh)
-        self._call("nb200_finalize_label_threshold", _ptr(self.hist), 1, _ptr(self.thr), _stream())
+        if self.nbins == 256:
+            self._call("nb200_finalize_label_threshold", _ptr(self.hist), 1, _ptr(self.thr), _stream())
+        else:
+            self._histn(log_domain=1, f64=0, otsu_only=0)
         out = self.thr.cpu().numpy()
         if out[3] != 0.0:
             return None
@@ -135,6 +152,10 @@ class LabelEngine:
         count = self._sample_hist(raw_f32, _cabi.TF_NONE, f64=integer_frame)
         if count == 0:
             return None
+        if self.nbins != 256:
+            self._histn(log_domain=0, f64=int(bool(integer_frame)), otsu_only=1)
+            v = self.thr.cpu().numpy()[0]
+            return np.float64(v) if integer_frame else np.float32(v)
         if integer_frame:
             self._call("nb200_finalize_otsu_f64", _ptr(self.hist), _ptr(self.thr), _stream())
             return np.float64(self.thr.cpu().numpy()[0])
@@ -165,8 +186,11 @@ class Label:
                              "nellie.segmentation.labelling.Label")
         if dev not in _DEVICES:
             raise ValueError(f"Unsupported device '{device}'. Use 'auto', 'gpu' or 'b200'.")
-        if int(histogram_nbins) != 256:
-            raise NotImplementedError("the device histogram is fixed at the reference default of 256 bins")
+        if int(histogram_nbins) < 2:
+            raise ValueError("histogram_nbins must be at least 2")
+        if int(histogram_nbins) != 256 and z_shard is not None:
+            raise NotImplementedError("the Z-sharded Label reduces the 256-bin histogram record; histogram_nbins != 256 is "
+                                      "supported for whole frames and T-sharded runs")
         self.im_info = im_info
         self.device = device
         self.device_type = "cuda"
@@ -186,7 +210,7 @@ class Label:
         x_res = im_info.dim_res.get("X") or 1.0
         self.min_radius_um = max(float(min_radius_um), float(x_res))     # labelling.py:95-97
         self.threshold_sampling_pixels = int(threshold_sampling_pixels)
-        self.histogram_nbins = 256
+        self.histogram_nbins = int(histogram_nbins)
         self.low_memory = bool(low_memory)
         self.max_chunk_voxels = int(max_chunk_voxels)
         self.ndim = 2 if im_info.no_z else 3
@@ -250,7 +274,7 @@ class Label:
             dev = self._torch_device()
             with torch.cuda.device(dev):
                 self._engine = LabelEngine(key, self.im_info.no_z, self.min_area_pixels,
-                                           self.threshold_sampling_pixels, dev)
+                                           self.threshold_sampling_pixels, dev, nbins=self.histogram_nbins)
         return self._engine
 
     def _dev_f32(self, arr):

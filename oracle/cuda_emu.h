@@ -72,5 +72,6 @@ inline unsigned grid_for(long long work_items, int threads, int ctas_per_sm) {
 #define nb_atomic_max_i32(p, v) do { if ((v) > *(p)) *(p) = (v); } while (0)
 #define nb_atomic_min_i32(p, v) do { if ((v) < *(p)) *(p) = (v); } while (0)
 #define nb_atomic_max_u64(p, v) do { if ((v) > *(p)) *(p) = (v); } while (0)
+#define nb_atomic_add_u64(p, v) do { *(p) += (v); } while (0)
 
 extern "C" const char* nb200_emu_last_error(void) { return nb::g_err; }

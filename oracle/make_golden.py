@@ -307,6 +307,30 @@ def network_frame_cases():
               f"branches={int(branch.max())} junction voxels={int((pixel_class == 4).sum())} relabelled voxels={int((relabelled > 0).sum())}")
 
 
+def label_nbins_cases():
+    """Label with histogram_nbins != 256 (labelling.py:23-35, :440-465), executed by the unmodified reference on the raw /
+    Frangi frames of existing fixtures: thresholds and labels only (the inputs stay in the parent fixture)."""
+    _, Label = ref_shim.load()
+    for name, parent, kw in (("label_nbins64_iso", "phantom3d_iso", dict(histogram_nbins=64)),
+                             ("label_nbins1000_iso", "phantom3d_iso", dict(histogram_nbins=1000)),
+                             ("label_nbins100_sample", "sample_crop", dict(histogram_nbins=100)),
+                             ("label_nbins33_2d", "phantom2d", dict(histogram_nbins=33)),
+                             ("label_nbins64_u16_otsu", "phantom3d_u16_otsu", dict(histogram_nbins=64, otsu_thresh_intensity=True)),
+                             ("label_nbins500_f32_otsu", "phantom3d_f32_otsu", dict(histogram_nbins=500, otsu_thresh_intensity=True))):
+        z = np.load(os.path.join(GOLDEN_DIR, f"{parent}.npz"))
+        meta = json.loads(str(z["meta"]))
+        info = ref_shim.im_info_for(z["raw"].shape, meta["dim_res"], meta["no_z"])
+        lab = Label(info, device="cpu", **kw)
+        lab.num_t = 1
+        it, ft = lab._compute_frame_thresholds(z["raw"], z["frangi"])
+        labels = lab._run_frame_full_volume(0, z["raw"], z["frangi"], it, ft)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"{name}.npz"), parent=np.asarray(parent),
+                            meta=np.asarray(json.dumps(dict(label_kwargs=kw))),
+                            intensity_thresh=np.float64(np.nan if it is None else it),
+                            frangi_thresh=np.float64(np.nan if ft is None else ft), labels=np.asarray(labels, np.int32))
+        print(f"{name}: it={it} ft={ft:.8g} labels={int(labels.max())} (256 bins: ft={float(z['frangi_thresh']):.8g})")
+
+
 def main():
     from nellie_b200.phantoms import tubular_phantom_np
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -351,6 +375,7 @@ def main():
     marker_cases()
     hu_cases()
     network_frame_cases()
+    label_nbins_cases()
 
 
 if __name__ == "__main__":
