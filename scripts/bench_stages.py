@@ -75,13 +75,22 @@ def main():
     meng = mk._engine_for(shape)
     raw_f = raw.contiguous()
     timed("markers.mask_border_distance", lambda: meng.distance_and_border(labels))
-    timed("markers.peaks_all_scales", lambda: meng.peaks(meng.distance))
+    checks = {}
     timed("markers.peaks_all_scales_two_step", lambda: meng.peaks(meng.distance, fused=False))
-    meng.peaks(meng.distance)
+    two_step = (meng.peak.clone(), meng.best.clone())
+    timed("markers.peaks_all_scales", lambda: meng.peaks(meng.distance))
+    checks["peaks_fused_equals_two_step"] = bool(torch.equal(meng.peak, two_step[0]) and torch.equal(meng.best, two_step[1]))
     timed("markers.suppress", lambda: meng.suppress(meng.peak, raw_f))
     timed("markers.frame", lambda: meng.run_frame(labels, raw_f))
     n_markers = int(meng.marker.sum().item())
     n_scales = len(meng.sigmas)
+    # size-independent properties of the reference's definitions (mocap_marking.py:419-450, :595-606)
+    fg = labels > 0
+    checks["markers_are_peaks_inside_the_mask"] = bool(((meng.marker == 0) | ((meng.peak != 0) & fg)).all().item())
+    checks["border_is_outside_the_mask_and_touches_it"] = bool(
+        ((meng.border == 0) | (~fg & (F.max_pool3d(fg[None, None].float(), 3, 1, 1)[0, 0] > 0))).all().item())
+    checks["distance_positive_exactly_on_the_mask"] = bool(torch.equal(meng.distance > 0, fg))
+    checks["distance_at_most_the_clamp"] = bool((meng.distance <= meng.clamp).all().item())
 
     # ---- HuMoment features (hu_tracking.py:585-680) ----
     hu = HuFeatureEngine(shape, False, dev)
@@ -103,6 +112,11 @@ def main():
     pixel_class = timed("network.pixel_class", lambda: net._get_pixel_class(skel_pre))
     branch = timed("network.branch_labels", lambda: net._get_branch_skel_labels(pixel_class))
     relabelled = timed("network.relabel_objects", lambda: neng.relabel(branch, labels, n_objects), reps=2)
+    # networking.py:485-577: seeds keep their own branch label; only object voxels of seeded objects are relabelled
+    seeds = (branch > 0) & fg
+    checks["relabel_keeps_seed_labels"] = bool(torch.equal(relabelled[seeds], branch[seeds]))
+    checks["relabel_stays_inside_objects"] = bool(((relabelled == 0) | fg).all().item())
+    checks["branch_labels_only_on_the_skeleton"] = bool(((branch == 0) | (skel_pre > 0)).all().item())
 
     vox = float(n) ** 3
     peak = 6530.3
@@ -120,6 +134,7 @@ def main():
         "markers": n_markers, "marker_scales": n_scales, "branches": int(branch.max().item()),
         "skeleton": "stand-in: ridge of the distance transform (the thinning is a scikit-image host call in the reference)",
         "relabelled_voxels": int((relabelled != 0).sum().item()), "relabel_crop_voxels_over_frame": neng.crop_voxels / vox,
+        "property_checks": checks,
         "ms": {k: round(v, 4) for k, v in times.items()},
         "voxels_per_s": {"markers.frame": vox / (times["markers.frame"] * 1e-3),
                          "network.device_steps": vox / (1e-3 * sum(v for k, v in times.items() if k.startswith("network.")))},

@@ -131,3 +131,4 @@ def test_bench_stages_script_runs_on_emulated_kernels(monkeypatch, capsys):
                 "network.relabel_objects", "network.add_missing"):
         assert key in line["ms"]
     assert line["objects"] >= 1 and line["relabelled_voxels"] > 0
+    assert len(line["property_checks"]) >= 8 and all(line["property_checks"].values()), line["property_checks"]
